@@ -1,0 +1,57 @@
+// Host front end of the B200 radiosity path: scene model held in host memory.
+// Mirrors the reference's global state (TriStore/trinum/G0/G1, rad.cpp:33-36, and the octree
+// file-statics raycast.cpp:9-16) as one object instead of globals.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "radk.h"
+
+namespace radk {
+
+static_assert(sizeof(radk_triangle) == 236, "radk_triangle must match the reference Triangle");
+static_assert(sizeof(radk_tree_node) == 60, "radk_tree_node must match the reference TreeNode");
+
+constexpr double kPi = 3.1415926535897932;	// rad.h:5
+constexpr int kRefMaxTri = 1000000;		// rad.h:9
+constexpr int kRefMaxTreeNode = 20000;		// rad.h:11
+constexpr int kMaxTriPerNode = 10;		// rad.h:12
+constexpr int kMaxLevel = 6;			// rad.h:7
+
+struct Model {
+	std::vector<radk_triangle> tri;		// size() == capacity of the pool; live slots [0, trinum)
+	int trinum = 0;
+	int n0 = 0;
+	float G0[3] = {0, 0, 0}, G1[3] = {0, 0, 0};
+	std::vector<radk_tree_node> nodes;
+	std::vector<int> list;
+	float min_grid_len = 0;
+	int grid_num = 0;
+	float min_area = 0, max_area = 0, sample_area = -1;
+	radk_model_opts opts{};
+
+	int pool_limit() const {
+		int mt = opts.max_tri > 0 ? opts.max_tri : kRefMaxTri;
+		return mt < opts.tri_limit ? mt : opts.tri_limit;
+	}
+};
+
+inline bool is_light(const radk_triangle &t) {	// rad.h:47-49
+	return t.Brgb[0] == 255 || t.Brgb[1] == 255 || t.Brgb[2] == 255;
+}
+
+void set_error(const std::string &msg);
+
+// tri_reader.cpp  (rad.cpp:47-111)
+int read_triangles(const char *text, size_t len, Model &m);
+// octree.cpp      (raycast.cpp:24-233)
+int build_octree(Model &m);
+// emitters.cpp    (rad.cpp:259-338)
+void init_radiosity(Model &m);
+// prepartition.cpp (shade.cpp:171-211, 311-431, 556-598)
+void prepartition(Model &m);
+// fin_writer.cpp  (rad.cpp:117-221 + float2string.h)
+void format_fin(const Model &m, std::string &out);
+int float_to_text(float v, char *buf);	// fp::tostring<float> equivalent; returns length, 0 = nothing written
+
+}  // namespace radk
