@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 shooting loop (BASELINE.json: visibility rays/sec and
+seconds-to-converge on church.tri), contract as described in the build brief.
+
+A "step" is one complete run of the hot path on the workload: rewind the radiosity state (device
+copy), flush L2, then shoot to convergence.  `value` is reference-equivalent visibility rays per
+second (one ray = one RayHitted call of the reference) with all inputs
+resident in HBM; `e2e` is the same metric through the C ABI with HOST buffers (state upload from the
+host TriStore image + loop + download inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+"""
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, Model kwargs, Context kwargs, description)
+    "church": ("church", {}, {}, "model/church.tri -triangle 1000000, default options, to convergence"),
+    "room": ("room", {}, {}, "model/room.tri -converge 1200 -delta_ff 0.000005, first 200 shots"),
+    "box": ("box", {}, {}, "model/box.tri default options, first 500 shots"),
+    "blocks": ("blocks", {}, {}, "model/blocks.tri frozen mesh, to convergence"),
+}
+SHOT_CAP = {"room": 200, "box": 500}
+ALGO_BYTES_PER_RECEIVER = 160
+
+
+def unpack_model(name, tmp):
+    path = os.path.join(tmp, name + ".tri")
+    with open(path, "wb") as f:
+        f.write(gzip.open(os.path.join(ROOT, "tests", "golden", "models", name + ".tri.gz")).read())
+    return path
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows, self.proc, self.device = [], None, device
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, idx in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > idx and r[idx].lower() == "active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(tri_path, shots, threads):
+    """The reference's own CPU implementation (oracle/_ref/ref_harness = unmodified sources, -O2
+    -ffp-contract=off -fopenmp) timed around its shot loop; falls back to the oracle port."""
+    from oracle import pyoracle as po
+    harness = po.ref_binary("ref_harness")
+    if harness:
+        args = [harness, "-jobs", str(threads), "-o", os.path.join(os.path.dirname(tri_path), "ref_out"), tri_path, "--json"]
+        if shots is not None:
+            args += ["--shots", str(shots)]
+        out = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout.decode(errors="replace")
+        info = json.loads([l for l in out.splitlines() if l.startswith("HARNESS_JSON")][0][len("HARNESS_JSON "):])
+        return {"kind": "reference", "rays": info["rays"], "seconds": info["loop_s"], "shots": info["shots"]}
+    import hw_radiosity_b200 as hr
+    m = hr.Model(tri_path)
+    s = m.scene
+    sc = po.Scene(m.triangles.copy(), m.n0, m.nodes.copy(), m.tri_list.copy(), s.G0, s.G1, s.min_grid_len, s.grid_num,
+                  threads=threads)
+    t = time.perf_counter()
+    seq = sc.run(shots)
+    dt = time.perf_counter() - t
+    return {"kind": "port", "rays": sc.stats["rays"], "seconds": dt, "shots": len(seq)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    model, _, _, desc = WORKLOADS[args.workload]
+    with tempfile.TemporaryDirectory() as tmp:
+        tri = unpack_model(model, tmp)
+        # bounded sample: size a step so that (steps + warmup) steps stay within ~3 minutes
+        probe = cpu_reference_run(tri, 10, threads)
+        per_shot = max(probe["seconds"] / max(probe["shots"], 1), 1e-6)
+        total = SHOT_CAP.get(args.workload)
+        budget = 150.0 / (args.steps + args.warmup)
+        shots = int(max(5, min(budget / per_shot, total or 10 ** 9)))
+        full = cpu_reference_run(tri, None, threads) if (total is None and budget / per_shot > 400) else None
+        if full is not None:
+            shots = None
+        for _ in range(args.warmup):
+            cpu_reference_run(tri, shots if shots else None, threads)
+        rays, secs, nshots = 0, 0.0, 0
+        for _ in range(args.steps):
+            r = cpu_reference_run(tri, shots if shots else None, threads)
+            rays += r["rays"]; secs += r["seconds"]; nshots = r["shots"]; kind = r["kind"]
+    value = rays / secs
+    sample = f"{model}.tri first {nshots} shots per step" if shots else f"{model}.tri to convergence ({nshots} shots) per step"
+    line = {
+        "impl": "reference", "metric": "visibility_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "repo model (tests/golden/models, gzip of the reference's model/*.tri)",
+        "config": {"workload": desc, "sample": sample, "threads": threads},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import hw_radiosity_b200 as hr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    model_name, mkw, ckw, desc = WORKLOADS[args.workload]
+    cap = SHOT_CAP.get(args.workload, -1)
+
+    with tempfile.TemporaryDirectory() as tmp:
+        tri = unpack_model(model_name, tmp)
+        model = hr.Model(tri, **mkw)
+        if world > 1:
+            raise SystemExit("multi-GPU bench arm not wired in this revision")
+        # reference-equivalent ray count of one step (deterministic): one statistics run, untimed
+        sctx = hr.Context(model, collect_stats=1, device=local_rank, **ckw)
+        sctx.step(cap)
+        st = sctx.stats()
+        rays_per_step, shots_per_step, recv_shaded = st["rays"], st["shots"], st["receivers"]
+        walk = {k: st[k] for k in ("traced_rays", "leaf_visits", "descent_steps", "tri_tests", "tri_accepts", "visible", "calff")}
+        sctx.close()
+
+        ctx = hr.Context(model, device=local_rank, **ckw)
+        sizes = ctx.sizes()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+        def one_step():
+            ctx.rewind()
+            flush.fill_(rank + 1)
+            torch.cuda.synchronize()
+            before = ctx.device_ms
+            done, conv = ctx.step(cap)
+            assert done == shots_per_step, (done, shots_per_step)
+            return ctx.device_ms - before
+
+        for _ in range(max(args.warmup, 3)):
+            one_step()
+        l0 = ctx.stats()["kernel_launches"]
+        torch.cuda.synchronize()
+        with ClockSampler(local_rank) as clk:
+            t0 = time.perf_counter()
+            dev_ms = [one_step() for _ in range(args.steps)]
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+        launches = ctx.stats()["kernel_launches"] - l0
+        ms_per_step = sum(dev_ms) / len(dev_ms)
+        value = rays_per_step / (ms_per_step / 1e3)
+
+        # per-kernel durations, live, CUDA events on the launching stream (first shots of a fresh run)
+        ctx.rewind()
+        kt = ctx.kernel_times(min(shots_per_step, 256))
+        ctx.rewind()
+
+        # end-to-end through the C ABI with host buffers: state upload + loop + download
+        def e2e_step():
+            t = time.perf_counter()
+            ctx.reset(model)                 # H2D: accB/deltaB of every receiver from the host TriStore image
+            ctx.step(cap)
+            ctx.download()                   # D2H: accB/deltaB of every receiver
+            return time.perf_counter() - t
+        for _ in range(2):
+            e2e_step()
+        e2e_s = sum(e2e_step() for _ in range(args.steps)) / args.steps
+        state_bytes = sizes["receivers"] * 48
+
+        # CPU baseline on this box's host cores (rank 0, N=1): the unmodified reference, bounded sample
+        threads = os.cpu_count() or 1
+        cpu_shots = None if args.workload in ("church", "blocks") else min(cap, 40)
+        cpu = cpu_reference_run(tri, cpu_shots, threads)
+
+    hbm_gbs, peak_src, sm_max = measured_peaks()
+    shot_ms = kt["k3a_ms"] + kt["k3b_ms"]
+    recv_per_shot = recv_shaded / max(shots_per_step, 1)
+    algo_bytes = ALGO_BYTES_PER_RECEIVER * recv_per_shot
+    dom = "vertex_ff_kernel (K3a)" if kt["k3a_ms"] >= kt["k3b_ms"] else "update_select_kernel (K3b)"
+    achieved = algo_bytes / (shot_ms * 1e-3) / 1e9 if shot_ms > 0 else 0.0
+    # FP32 side of the SURVEY section 8(d) roofline, counted per traced ray by the device itself
+    flops = (35 * walk["calff"] + 12 * walk["leaf_visits"] + 6 * walk["descent_steps"] + 22 * (walk["leaf_visits"] - walk["tri_accepts"] * 0)
+             + 14 * walk["tri_tests"] + 24 * walk["tri_accepts"])
+    p_fp32 = 148 * 128 * 2 * sm_max * 1e6
+    line = {
+        "metric": "visibility_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "repo model (tests/golden/models, gzip of the reference's model/*.tri)",
+        "config": {"workload": desc, "receivers": sizes["receivers"], "unique_vertices": sizes["unique_vertices"],
+                   "shots_per_step": shots_per_step, "reference_equivalent_rays_per_step": rays_per_step,
+                   "traced_rays_per_step": walk["traced_rays"], "l2": "flushed between steps (256 MiB write), state rewound on device",
+                   "timing": "per-step CUDA-event windows around radk_ctx_step on its stream, mean of K steps",
+                   "parity": "bit-exact mode (-fmad=false)"},
+        "seconds_to_converge": ms_per_step / 1e3 if cap < 0 else None,
+        "wall_s_timed_region": wall,
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "e2e": {"value": rays_per_step / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": state_bytes,
+                "d2h_bytes_per_step": state_bytes, "seconds_per_step": e2e_s},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                     "traffic": None, "kernel": dom, "peak_source": peak_src,
+                     "note": "algorithmic bytes = 160 B x shaded receivers per shot over the K3a+K3b pair of one shot; "
+                             "church is FP32-issue/latency bound (SURVEY 8d), see fp32",
+                     "k3a_ms": kt["k3a_ms"], "k3b_ms": kt["k3b_ms"], "shots_profiled": kt["shots"]},
+        "fp32": {"flops_per_step_counted": flops, "achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
+                 "peak_tflops": p_fp32 / 1e12, "frac": flops / (ms_per_step * 1e-3) / p_fp32},
+        "cpu_baseline": {"value": cpu["rays"] / cpu["seconds"], "unit": "rays/s", "cores": threads, "kind": cpu["kind"],
+                         "sample": f"{model_name}.tri, {cpu['shots']} shots, shot loop only ({cpu['seconds']:.2f} s)",
+                         "seconds": cpu["seconds"]},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="church", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

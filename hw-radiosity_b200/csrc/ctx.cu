@@ -1,0 +1,537 @@
+// Device context of the shooting loop: scene upload (flattening the octree, sorting receivers,
+// sharing vertices), the shot loop, downloads, and the C ABI declared in include/radk.h.
+//
+// Everything that computes runs in the kernels of shoot_kernels.cuh; there is no CPU fallback -
+// every entry point fails with RADK_ERR_CUDA when no device is usable.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "radk.h"
+#include "shoot_kernels.cuh"
+#include "scene_flatten.hpp"
+
+namespace radk {
+void set_error(const std::string &msg);	// host/model_capi.cpp
+}
+
+using namespace radk;
+
+#define CUDA_TRY(expr)                                                                             \
+	do {                                                                                       \
+		cudaError_t e_ = (expr);                                                           \
+		if (e_ != cudaSuccess) {                                                           \
+			set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+			return RADK_ERR_CUDA;                                                      \
+		}                                                                                  \
+	} while (0)
+
+namespace {
+
+template <typename T> struct DevBuf {
+	T *p = nullptr;
+	size_t n = 0;
+	cudaError_t alloc(size_t count) {
+		release();
+		n = count;
+		return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+	}
+	cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
+		cudaError_t e = alloc(h.size());
+		if (e != cudaSuccess || h.empty()) return e;
+		return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct radk_ctx {
+	radk_opts opt{};
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double device_ms = 0;
+	long long launches = 0;
+
+	int trinum = 0, n0 = 0;
+	int R = 0, U = 0, leaves_total = 0;
+	std::vector<int> recv_slot;		// receiver index -> slot (this shard)
+	std::vector<int> recv_parent;
+
+	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot;
+	DevBuf<float4> leaf_lo, leaf_hi, occ, geo[3], st[3], st0[3], uv, par_n, par_fk;
+	DevBuf<int4> vid;
+	DevBuf<float2> ffh;
+	DevBuf<unsigned> vstat, partial_cnt, ticket;
+	DevBuf<unsigned long long> partial_key, bound;
+	DevBuf<int> flags;			// [0]=ncand [1]=nsrc [2]=converged
+	DevBuf<long long> shots_done;
+	DevBuf<DevStats> stats;
+	DevBuf<ShooterRec> rec;			// [0],[1]: ping-pong for the single-source loop; [2..]: multi-source list
+	DevBuf<radk_candidate> cand;		// multi-GPU exchange buffer [world]
+	int max_blocks = 0;
+	int cur = 0;				// which of rec[0]/rec[1] holds the current shooter
+	bool have_current = false;		// rec[cur] is up to date with the device state
+	DevScene S{};
+	struct HostFlags { int ncand, nsrc, converged; } *h_flags = nullptr;	// pinned
+	long long *h_shots = nullptr;		// pinned
+	bool use_dedup = true;
+};
+
+namespace {
+
+const int kShotLogCap = 1 << 20;
+const int kBatchShots = 32;
+
+int upload_scene(radk_ctx *c, const radk_scene *s) {
+	const radk_opts &o = c->opt;
+	cudaStream_t st = c->stream;
+	c->trinum = s->trinum;
+	c->n0 = s->n0;
+	const int world = std::max(1, o.world);
+	FlatScene F;
+	const int frc = flatten_scene(s, o.rank, world, F);
+	if (frc != RADK_OK) { set_error(F.error); return frc; }
+	const int R = F.R, U = F.U;
+	c->R = R, c->U = U, c->leaves_total = F.leaves_total;
+	c->recv_slot = F.recv_slot;
+	c->recv_parent = F.recv_parent;
+	CUDA_TRY(c->cell_leaf.upload(F.cell_leaf, st));
+	CUDA_TRY(c->leaf_lo.upload(F.leaf_lo, st));
+	CUDA_TRY(c->leaf_hi.upload(F.leaf_hi, st));
+	CUDA_TRY(c->list.upload(F.list, st));
+	CUDA_TRY(c->occ.upload(F.occ, st));
+	for (int v = 0; v < 3; v++) {
+		CUDA_TRY(c->geo[v].upload(F.geo[v], st));
+		CUDA_TRY(c->st[v].upload(F.st[v], st));
+		CUDA_TRY(c->st0[v].upload(F.st[v], st));
+	}
+	CUDA_TRY(c->slot_to_recv.upload(F.slot_to_recv, st));
+	CUDA_TRY(c->slot.upload(F.recv_slot, st));
+	CUDA_TRY(c->par_n.upload(F.par_n, st));
+	CUDA_TRY(c->par_fk.upload(F.par_fk, st));
+	CUDA_TRY(c->vid.upload(F.vid, st));
+	CUDA_TRY(c->uv.upload(F.uv, st));
+	CUDA_TRY(c->ffh.alloc(U));
+	CUDA_TRY(c->vstat.alloc(U));
+	CUDA_TRY(cudaMemsetAsync(c->ffh.p, 0, std::max(U, 1) * sizeof(float2), st));
+	CUDA_TRY(cudaMemsetAsync(c->vstat.p, 0, std::max(U, 1) * sizeof(unsigned), st));
+
+	// ---- selection / bookkeeping state
+	c->max_blocks = std::max(1, (R + 255) / 256);
+	CUDA_TRY(c->partial_key.alloc(c->max_blocks));
+	CUDA_TRY(c->partial_cnt.alloc(c->max_blocks));
+	CUDA_TRY(c->ticket.alloc(1));
+	CUDA_TRY(c->bound.alloc(1));
+	CUDA_TRY(c->flags.alloc(4));
+	CUDA_TRY(c->shots_done.alloc(1));
+	CUDA_TRY(c->shot_log.alloc(kShotLogCap));
+	CUDA_TRY(c->stats.alloc(1));
+	CUDA_TRY(c->rec.alloc(2 + kMaxSources));
+	CUDA_TRY(c->cand.alloc(world));
+	CUDA_TRY(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned), st));
+	CUDA_TRY(cudaMemsetAsync(c->bound.p, 0xff, sizeof(unsigned long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->stats.p, 0, sizeof(DevStats), st));
+	CUDA_TRY(cudaMemsetAsync(c->rec.p, 0, (2 + kMaxSources) * sizeof(ShooterRec), st));
+	CUDA_TRY(cudaMemsetAsync(c->cand.p, 0, world * sizeof(radk_candidate), st));
+
+	DevScene &S = c->S;
+	S.tree.cell_leaf = c->cell_leaf.p;
+	S.tree.leaf_lo = c->leaf_lo.p;
+	S.tree.leaf_hi = c->leaf_hi.p;
+	S.tree.list = c->list.p;
+	S.tree.occ = c->occ.p;
+	for (int k = 0; k < 3; k++) S.tree.G0[k] = s->G0[k], S.tree.G1[k] = s->G1[k];
+	S.tree.min_grid_len = s->min_grid_len;
+	S.tree.grid_num = s->grid_num;
+	S.R = R, S.U = U, S.n0 = s->n0;
+	for (int v = 0; v < 3; v++) S.geo[v] = c->geo[v].p, S.st[v] = c->st[v].p;
+	S.vid = c->vid.p, S.slot = c->slot.p, S.uv = c->uv.p, S.ffh = c->ffh.p, S.vstat = c->vstat.p;
+	S.par_n = c->par_n.p, S.par_fk = c->par_fk.p, S.slot_to_recv = c->slot_to_recv.p;
+	S.converge = o.converge;
+	S.parallel_src = std::max(1, std::min(o.parallel_src, kMaxSources));
+	S.stats = c->stats.p;
+	S.sel.partial_key = c->partial_key.p, S.sel.partial_cnt = c->partial_cnt.p, S.sel.ticket = c->ticket.p;
+	S.sel.bound = c->bound.p;
+	S.sel.ncand = c->flags.p, S.sel.nsrc = c->flags.p + 1, S.sel.converged = c->flags.p + 2;
+	S.sel.shots_done = c->shots_done.p;
+	S.sel.shot_log = c->shot_log.p, S.sel.shot_log_cap = kShotLogCap;
+	CUDA_TRY(cudaStreamSynchronize(st));
+	c->have_current = false;
+	c->cur = 0;
+	return RADK_OK;
+}
+
+inline int blocks_for(int n, int bs) { return std::max(1, (n + bs - 1) / bs); }
+
+// K1 stand-alone: (re)select the current shooter into rec[cur]
+void launch_select(radk_ctx *c, ShooterRec *out, int which) {
+	select_kernel<<<std::min(c->max_blocks, 4 * 148), 256, 0, c->stream>>>(c->S, out, which);
+	c->launches++;
+}
+
+void launch_single_source_shot(radk_ctx *c) {
+	const bool stats = c->opt.collect_stats != 0;
+	ShooterRec *cur = c->rec.p + c->cur, *nxt = c->rec.p + (c->cur ^ 1);
+	const int nb_v = blocks_for(2 * c->U, 128);
+	if (stats) vertex_ff_kernel<true><<<nb_v, 128, 0, c->stream>>>(c->S, cur);
+	else vertex_ff_kernel<false><<<nb_v, 128, 0, c->stream>>>(c->S, cur);
+	const int nb_u = blocks_for(c->R, 256);
+	if (stats) update_select_kernel<true><<<nb_u, 256, 0, c->stream>>>(c->S, cur, nxt);
+	else update_select_kernel<false><<<nb_u, 256, 0, c->stream>>>(c->S, cur, nxt);
+	c->cur ^= 1;
+	c->launches += 2;
+}
+
+void launch_multi_source_iteration(radk_ctx *c) {
+	const bool stats = c->opt.collect_stats != 0;
+	ShooterRec *list = c->rec.p + 2;
+	const int P = c->S.parallel_src;
+	for (int j = 0; j < P; j++) launch_select(c, list + j, j);
+	const int nb = blocks_for(c->R, 128);
+	if (stats) shade_receivers_kernel<true><<<nb, 128, 0, c->stream>>>(c->S, list, P);
+	else shade_receivers_kernel<false><<<nb, 128, 0, c->stream>>>(c->S, list, P);
+	after_generic_pass_kernel<<<1, 1, 0, c->stream>>>(c->S, list);
+	c->launches += 2;
+}
+
+int read_flags(radk_ctx *c) {
+	CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags.p, sizeof(*c->h_flags), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->h_shots, c->shots_done.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return RADK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int radk_ctx_create(const radk_scene *s, const radk_opts *o, radk_ctx **out) {
+	if (!s || !out || !s->tri || !s->nodes || !s->list) { set_error("radk_ctx_create: null argument"); return RADK_ERR_ARG; }
+	radk_opts opt;
+	if (o) opt = *o; else radk_default_opts(&opt);
+	if (opt.world <= 0) opt.world = 1;
+	if (opt.rank < 0 || opt.rank >= opt.world) { set_error("radk_ctx_create: rank outside [0, world)"); return RADK_ERR_ARG; }
+	if (opt.split_enabled) { set_error("radk_ctx_create: adaptive splitting is not available in this build"); return RADK_ERR_STATE; }
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		set_error(std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+		return RADK_ERR_CUDA;
+	}
+	CUDA_TRY(cudaSetDevice(opt.device));
+	radk_ctx *c = new radk_ctx();
+	c->opt = opt;
+	c->device = opt.device;
+	c->use_dedup = opt.dedup >= 0 && opt.parallel_src <= 1;
+	int rc = RADK_OK;
+	do {
+		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+		    cudaMallocHost((void **)&c->h_flags, sizeof(*c->h_flags)) != cudaSuccess ||
+		    cudaMallocHost((void **)&c->h_shots, sizeof(long long)) != cudaSuccess) {
+			set_error(std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()));
+			rc = RADK_ERR_CUDA;
+			break;
+		}
+		rc = upload_scene(c, s);
+	} while (0);
+	if (rc != RADK_OK) { radk_ctx_destroy(c); return rc; }
+	*out = c;
+	return RADK_OK;
+}
+
+void radk_ctx_destroy(radk_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->h_flags) cudaFreeHost(c->h_flags);
+	if (c->h_shots) cudaFreeHost(c->h_shots);
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int radk_ctx_reset(radk_ctx *c, const radk_scene *s) {
+	if (!c || !s) { set_error("radk_ctx_reset: null argument"); return RADK_ERR_ARG; }
+	if (s->trinum != c->trinum) { set_error("radk_ctx_reset: scene size changed"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	std::vector<float4> stt(c->R);
+	for (int v = 0; v < 3; v++) {
+		for (int r = 0; r < c->R; r++) {
+			const radk_triangle &t = s->tri[c->recv_slot[r]];
+			stt[r] = make_float4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
+		}
+		CUDA_TRY(cudaMemcpyAsync(c->st[v].p, stt.data(), (size_t)c->R * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->st0[v].p, c->st[v].p, (size_t)c->R * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+	}
+	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->stats.p, 0, sizeof(DevStats), c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->have_current = false;
+	c->device_ms = 0;
+	return RADK_OK;
+}
+
+int radk_ctx_rewind(radk_ctx *c) {
+	if (!c) { set_error("radk_ctx_rewind: null context"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	for (int v = 0; v < 3; v++)
+		CUDA_TRY(cudaMemcpyAsync(c->st[v].p, c->st0[v].p, (size_t)c->R * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->have_current = false;
+	return RADK_OK;
+}
+
+int radk_ctx_sizes(const radk_ctx *c, int *receivers, int *unique_vertices, int *occluders, int *nodes) {
+	if (!c) { set_error("radk_ctx_sizes: null context"); return RADK_ERR_ARG; }
+	if (receivers) *receivers = c->R;
+	if (unique_vertices) *unique_vertices = c->U;
+	if (occluders) *occluders = c->n0;
+	if (nodes) *nodes = (int)c->leaf_lo.n;
+	return RADK_OK;
+}
+
+int radk_ctx_kernel_times(radk_ctx *c, int nshots, double *k3a_ms, double *k3b_ms, int *shots_run) {
+	if (!c || nshots <= 0) { set_error("radk_ctx_kernel_times: bad argument"); return RADK_ERR_ARG; }
+	if (!c->use_dedup) { set_error("radk_ctx_kernel_times: single-source contexts only"); return RADK_ERR_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	int rc = read_flags(c);
+	if (rc) return rc;
+	const long long before = *c->h_shots;
+	if (!c->have_current) { launch_select(c, c->rec.p + c->cur, 0); c->have_current = true; }
+	std::vector<cudaEvent_t> ev((size_t)nshots * 3);
+	for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+	const bool stats = c->opt.collect_stats != 0;
+	for (int i = 0; i < nshots; i++) {
+		ShooterRec *cur = c->rec.p + c->cur, *nxt = c->rec.p + (c->cur ^ 1);
+		CUDA_TRY(cudaEventRecord(ev[3 * i], c->stream));
+		if (stats) vertex_ff_kernel<true><<<blocks_for(2 * c->U, 128), 128, 0, c->stream>>>(c->S, cur);
+		else vertex_ff_kernel<false><<<blocks_for(2 * c->U, 128), 128, 0, c->stream>>>(c->S, cur);
+		CUDA_TRY(cudaEventRecord(ev[3 * i + 1], c->stream));
+		if (stats) update_select_kernel<true><<<blocks_for(c->R, 256), 256, 0, c->stream>>>(c->S, cur, nxt);
+		else update_select_kernel<false><<<blocks_for(c->R, 256), 256, 0, c->stream>>>(c->S, cur, nxt);
+		CUDA_TRY(cudaEventRecord(ev[3 * i + 2], c->stream));
+		c->cur ^= 1;
+		c->launches += 2;
+	}
+	if ((rc = read_flags(c))) return rc;
+	const int ran = (int)(*c->h_shots - before);
+	double a = 0, b = 0;
+	for (int i = 0; i < ran; i++) {
+		float m1 = 0, m2 = 0;
+		CUDA_TRY(cudaEventElapsedTime(&m1, ev[3 * i], ev[3 * i + 1]));
+		CUDA_TRY(cudaEventElapsedTime(&m2, ev[3 * i + 1], ev[3 * i + 2]));
+		a += m1, b += m2;
+	}
+	for (auto &e : ev) cudaEventDestroy(e);
+	if (k3a_ms) *k3a_ms = ran ? a / ran : 0;
+	if (k3b_ms) *k3b_ms = ran ? b / ran : 0;
+	if (shots_run) *shots_run = ran;
+	return RADK_OK;
+}
+
+int radk_ctx_step(radk_ctx *c, long long max_shots, long long *shots_done, int *converged) {
+	if (!c) { set_error("radk_ctx_step: null context"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	long long before = 0;
+	int rc = read_flags(c);
+	if (rc) return rc;
+	before = *c->h_shots;
+	long long done = 0;
+	int conv = 0;
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	if (c->use_dedup) {
+		if (!c->have_current) { launch_select(c, c->rec.p + c->cur, 0); c->have_current = true; }
+		while (max_shots < 0 || done < max_shots) {
+			long long batch = kBatchShots;
+			if (max_shots >= 0) batch = std::min<long long>(batch, max_shots - done);
+			for (long long i = 0; i < batch; i++) launch_single_source_shot(c);
+			if ((rc = read_flags(c))) return rc;
+			done = *c->h_shots - before;
+			if (c->h_flags->converged) { conv = 1; break; }
+		}
+	} else {
+		while (max_shots < 0 || done < max_shots) {
+			long long batch = std::min<long long>(kBatchShots, max_shots < 0 ? kBatchShots : max_shots - done);
+			for (long long i = 0; i < batch; i++) launch_multi_source_iteration(c);
+			if ((rc = read_flags(c))) return rc;
+			done = *c->h_shots - before;
+			if (c->h_flags->converged) { conv = 1; break; }
+		}
+		c->have_current = false;
+	}
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+	CUDA_TRY(cudaEventSynchronize(c->ev1));
+	float ms = 0;
+	CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+	c->device_ms += ms;
+	CUDA_TRY(cudaGetLastError());
+	if (shots_done) *shots_done = done;
+	if (converged) *converged = conv;
+	return RADK_OK;
+}
+
+int radk_ctx_select(radk_ctx *c, int *slots, int cap, int *n) {
+	if (!c || !n) { set_error("radk_ctx_select: null argument"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	ShooterRec *list = c->rec.p + 2;
+	const int P = c->S.parallel_src;
+	for (int j = 0; j < P; j++) launch_select(c, list + j, j);
+	int rc = read_flags(c);
+	if (rc) return rc;
+	std::vector<ShooterRec> h(P);
+	CUDA_TRY(cudaMemcpy(h.data(), list, P * sizeof(ShooterRec), cudaMemcpyDeviceToHost));
+	int k = 0;
+	for (int j = 0; j < c->h_flags->nsrc && j < P; j++)
+		if (h[j].valid && k < cap && slots) slots[k++] = h[j].slot;
+	*n = std::min(c->h_flags->nsrc, P);
+	c->have_current = false;	// flags.converged was rewritten by the stand-alone selection
+	return RADK_OK;
+}
+
+int radk_ctx_shooter_log(radk_ctx *c, int *slots, int cap, long long *n) {
+	if (!c || !n) { set_error("radk_ctx_shooter_log: null argument"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	int rc = read_flags(c);
+	if (rc) return rc;
+	*n = *c->h_shots;
+	const long long have = std::min<long long>(*n, kShotLogCap);
+	const long long want = std::min<long long>(have, cap);
+	if (slots && want > 0) {
+		std::vector<int> ring(kShotLogCap);
+		CUDA_TRY(cudaMemcpy(ring.data(), c->shot_log.p, sizeof(int) * (size_t)std::min<long long>(*n, kShotLogCap), cudaMemcpyDeviceToHost));
+		for (long long i = 0; i < want; i++) slots[i] = ring[(size_t)((*n - want + i) % kShotLogCap)];
+	}
+	return RADK_OK;
+}
+
+int radk_ctx_trinum(const radk_ctx *c) { return c ? c->trinum : -1; }
+
+int radk_ctx_download(radk_ctx *c, float *accB, float *deltaB, int *parent, int trinum) {
+	if (!c) { set_error("radk_ctx_download: null context"); return RADK_ERR_ARG; }
+	if (trinum < c->trinum) { set_error("radk_ctx_download: buffers smaller than trinum"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	std::vector<float4> h[3];
+	for (int v = 0; v < 3; v++) {
+		h[v].resize(c->R);
+		CUDA_TRY(cudaMemcpyAsync(h[v].data(), c->st[v].p, (size_t)c->R * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	}
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	for (int r = 0; r < c->R; r++) {
+		const int slot = c->recv_slot[r];
+		for (int v = 0; v < 3; v++) {
+			if (accB) {
+				accB[(size_t)slot * 9 + v * 3 + 0] = h[v][r].x;
+				accB[(size_t)slot * 9 + v * 3 + 1] = h[v][r].y;
+				accB[(size_t)slot * 9 + v * 3 + 2] = h[v][r].z;
+			}
+			if (deltaB) deltaB[(size_t)slot * 3 + v] = h[v][r].w;
+		}
+		if (parent) parent[slot] = c->recv_parent[r];
+	}
+	return RADK_OK;
+}
+
+int radk_ctx_download_triangles(radk_ctx *c, radk_triangle *tri, int cap, int *trinum) {
+	(void)tri; (void)cap; (void)trinum;
+	if (!c) { set_error("radk_ctx_download_triangles: null context"); return RADK_ERR_ARG; }
+	set_error("radk_ctx_download_triangles: only meaningful for adaptive-split contexts");
+	return RADK_ERR_STATE;
+}
+
+int radk_ctx_snapshot_colors(radk_ctx *c, int *rgb, int trinum) {
+	if (!c || !rgb) { set_error("radk_ctx_snapshot_colors: null argument"); return RADK_ERR_ARG; }
+	if (trinum < c->trinum) { set_error("radk_ctx_snapshot_colors: buffer smaller than trinum"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	DevBuf<int> d;
+	CUDA_TRY(d.alloc((size_t)c->R * 3));
+	snapshot_kernel<<<blocks_for(c->R, 256), 256, 0, c->stream>>>(c->S, d.p);
+	c->launches++;
+	std::vector<int> h((size_t)c->R * 3);
+	CUDA_TRY(cudaMemcpyAsync(h.data(), d.p, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	for (int i = 0; i < c->trinum; i++) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = -1;
+	for (int r = 0; r < c->R; r++)
+		for (int j = 0; j < 3; j++) rgb[(size_t)c->recv_slot[r] * 3 + j] = h[(size_t)r * 3 + j];
+	return RADK_OK;
+}
+
+int radk_ctx_stats(radk_ctx *c, radk_stats *out) {
+	if (!c || !out) { set_error("radk_ctx_stats: null argument"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	DevStats h;
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaMemcpy(&h, c->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+	memset(out, 0, sizeof(*out));
+	out->shots = (long long)h.shots;
+	out->rays = (long long)h.rays, out->visible = (long long)h.visible, out->calff = (long long)h.calff;
+	out->traced_rays = (long long)h.traced;
+	out->leaf_visits = (long long)h.leaf_visits, out->descent_steps = (long long)h.descent_steps;
+	out->tri_tests = (long long)h.tri_tests, out->tri_accepts = (long long)h.tri_accepts;
+	out->precision_exceeded = (long long)h.precision_exceeded;
+	out->receivers = (long long)h.receivers, out->splits = (long long)h.splits;
+	out->kernel_launches = c->launches;
+	out->ray_guard_trips = (long long)h.guard_trips;
+	return RADK_OK;
+}
+
+double radk_ctx_device_ms(const radk_ctx *c) { return c ? c->device_ms : 0.0; }
+
+int radk_ctx_shoot(radk_ctx *c, const int *slots, int n) {
+	if (!c || !slots || n <= 0 || n > kMaxSources) { set_error("radk_ctx_shoot: bad argument"); return RADK_ERR_ARG; }
+	set_error("radk_ctx_shoot: not implemented yet");
+	return RADK_ERR_STATE;
+}
+
+int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from, int n, int *hit) {
+	if (!c || !p || !v || !from || !hit || n < 0) { set_error("radk_ray_hitted: bad argument"); return RADK_ERR_ARG; }
+	if (n == 0) return RADK_OK;
+	CUDA_TRY(cudaSetDevice(c->device));
+	DevBuf<float> dp, dv;
+	DevBuf<int> df, dh;
+	CUDA_TRY(dp.alloc((size_t)n * 3));
+	CUDA_TRY(dv.alloc((size_t)n * 3));
+	CUDA_TRY(df.alloc(n));
+	CUDA_TRY(dh.alloc(n));
+	CUDA_TRY(cudaMemcpyAsync(dp.p, p, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(dv.p, v, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(df.p, from, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+	ray_batch_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->S.tree, dp.p, dv.p, df.p, n, dh.p);
+	c->launches++;
+	CUDA_TRY(cudaMemcpyAsync(hit, dh.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	return RADK_OK;
+}
+
+int radk_vertex_ff(radk_ctx *c, int shooter, const int *receiver, const int *vertex, int n, float *ff) {
+	if (!c || !receiver || !vertex || !ff || n < 0) { set_error("radk_vertex_ff: bad argument"); return RADK_ERR_ARG; }
+	if (shooter < 0 || shooter >= c->trinum) { set_error("radk_vertex_ff: shooter slot out of range"); return RADK_ERR_ARG; }
+	set_error("radk_vertex_ff: not implemented yet");
+	return RADK_ERR_STATE;
+}
+
+int radk_ctx_local_candidate(radk_ctx *c, radk_candidate *out) { (void)c; (void)out; set_error("not implemented yet"); return RADK_ERR_STATE; }
+int radk_ctx_shoot_candidate(radk_ctx *c, const radk_candidate *s) { (void)c; (void)s; set_error("not implemented yet"); return RADK_ERR_STATE; }
+int radk_ctx_candidate_buffer(radk_ctx *c, void **p, size_t *b) { (void)c; (void)p; (void)b; set_error("not implemented yet"); return RADK_ERR_STATE; }
+int radk_ctx_local_candidate_dev(radk_ctx *c, void *s) { (void)c; (void)s; set_error("not implemented yet"); return RADK_ERR_STATE; }
+int radk_ctx_shoot_gathered_dev(radk_ctx *c, void *s) { (void)c; (void)s; set_error("not implemented yet"); return RADK_ERR_STATE; }
+int radk_ctx_converged_flag(radk_ctx *c, int *conv) { (void)c; (void)conv; set_error("not implemented yet"); return RADK_ERR_STATE; }
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+// Device core of the shooting loop: octree walk, triangle test, form factor.
+//
+// Arithmetic contract: every expression follows the reference's C++
+// (src/raycast.cpp:235-360, src/shade.cpp:107-168) operation by operation - float unless the
+// reference promotes through a double literal - evaluated left to right.  The translation unit
+// is compiled with -fmad=false (no contraction), IEEE division and square root, no FTZ, so the
+// results are bit-identical to the reference built with -ffp-contract=off.
+//
+// The functions are __host__ __device__ so that tests/hostemu can run exactly this code on the
+// CPU against the oracle when no GPU is present; the product only ever calls them from kernels.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define RADK_HD __host__ __device__ __forceinline__
+#else
+#define RADK_HD inline
+struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+#endif
+
+namespace radk {
+
+// ---- flattened scene, as laid out in HBM by scene_upload (ctx.cu) -------------------------------
+// The reference's pointer-chasing root descent (TreeNodeNum, raycast.cpp:266-278) is replaced by a
+// dense table over the finest grid: cell (gx,gy,gz) -> leaf node, built on the host by running the
+// reference descent for every cell, so the leaf found is the same by construction.
+struct DevTree {
+	const int *cell_leaf;		// [(grid_num+1)^3], x fastest
+	const float4 *leaf_lo;		// per node: g0.xyz | list offset (int bits)
+	const float4 *leaf_hi;		// per node: g1.xyz | depth (int bits, statistics only)
+	const int *list;		// leaf lists, -1 terminated, ascending triangle index
+	const float4 *occ;		// 5 float4 per occluder, see OCC_* below
+	float G0[3], G1[3];
+	float min_grid_len;
+	int grid_num;
+};
+// occluder record (the {n, c, se} of TriStore[idx] at shot time, raycast.cpp:288-309):
+//   q0 = n.x n.y n.z c.x | q1 = c.y c.z se00 se01 | q2 = se02 se03 se10 se11
+//   q3 = se12 se13 se20 se21 | q4 = se22 se23 - -
+constexpr int OCC_STRIDE = 5;
+
+struct WalkCounters {
+	unsigned traced, leaf_visits, descent_steps, tri_tests, tri_accepts, precision_exceeded, guard_trips;
+};
+
+RADK_HD int float_as_int_hd(float f) {
+#if defined(__CUDA_ARCH__)
+	return __float_as_int(f);
+#else
+	union { float f; int i; } u; u.f = f; return u.i;
+#endif
+}
+RADK_HD float int_as_float_hd(int i) {
+#if defined(__CUDA_ARCH__)
+	return __int_as_float(i);
+#else
+	union { float f; int i; } u; u.i = i; return u.f;
+#endif
+}
+template <typename T> RADK_HD T ldg(const T *p) {
+#if defined(__CUDA_ARCH__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
+
+// vector.h:36 InnerProd
+RADK_HD float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+	return ax * bx + ay * by + az * bz;
+}
+
+// TreeNodeNum (raycast.cpp:254-281): leaf containing q, or -1 outside the scene cube.
+template <bool STATS>
+RADK_HD int leaf_of(const DevTree &T, float qx, float qy, float qz, WalkCounters *wc) {
+	if (qx < T.G0[0] || qx > T.G1[0] || qy < T.G0[1] || qy > T.G1[1] || qz < T.G0[2] || qz > T.G1[2])
+		return -1;
+	int gx = (int)(((double)qx - (double)T.G0[0]) / (double)T.min_grid_len);
+	int gy = (int)(((double)qy - (double)T.G0[1]) / (double)T.min_grid_len);
+	int gz = (int)(((double)qz - (double)T.G0[2]) / (double)T.min_grid_len);
+	// every index >= grid_num takes the all-upper path of the descent, negatives the all-lower one
+	const int g = T.grid_num, dim = g + 1;
+	gx = gx < 0 ? 0 : (gx > g ? g : gx);
+	gy = gy < 0 ? 0 : (gy > g ? g : gy);
+	gz = gz < 0 ? 0 : (gz > g ? g : gz);
+	const int leaf = ldg(&T.cell_leaf[(gz * dim + gy) * dim + gx]);
+	if (STATS) wc->descent_steps += (unsigned)float_as_int_hd(ldg(&T.leaf_hi[leaf]).w);
+	return leaf;
+}
+
+// TriHitted (raycast.cpp:283-313)
+RADK_HD bool tri_hit(const float4 *o, float px, float py, float pz, float vx, float vy, float vz, float &t_min) {
+	const float4 q0 = ldg(o), q1 = ldg(o + 1);
+	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
+	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
+	const float t = a2 / a1;
+	if ((double)t < 0.0001) return false;
+	if (t >= t_min) return false;
+	const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
+	const float4 q2 = ldg(o + 2);
+	if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) return false;
+	const float4 q3 = ldg(o + 3);
+	if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) return false;
+	const float4 q4 = ldg(o + 4);
+	if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) return false;
+	t_min = t;
+	return true;
+}
+
+// RayHitted (raycast.cpp:335-360) with TriListHitted (316-333) and NextPoint (235-251) inlined.
+// Returns the triangle index hit in the first leaf (in stepping order) that has any hit, or -1.
+template <bool STATS>
+RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, float vy, float vz, int ban,
+		     WalkCounters *wc) {
+	float t = 0.f;
+	int prev = -1, cur;
+	float qx = px, qy = py, qz = pz;
+	int guard = 0;
+	if (STATS) wc->traced++;
+	while ((cur = leaf_of<STATS>(T, qx, qy, qz, wc)) >= 0) {
+		if (prev == cur) {		// raycast.cpp:344-351 "Precision Exceeded"
+			if (STATS) wc->precision_exceeded++;
+			t = (float)((double)t + 1.0);
+			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
+			if (++guard > 100000) {	// the reference would spin forever
+				if (STATS) wc->guard_trips++;
+				return -1;
+			}
+			continue;
+		}
+		const float4 lo = ldg(&T.leaf_lo[cur]);
+		const float4 hi = ldg(&T.leaf_hi[cur]);
+		if (STATS) wc->leaf_visits++;
+		// TriListHitted
+		int hit = -1;
+		float t_min = 1000000.0f;
+		const int *lp = T.list + float_as_int_hd(lo.w);
+		int idx;
+		while ((idx = ldg(lp++)) >= 0) {
+			if (idx == ban) continue;
+			if (STATS) wc->tri_tests++;
+			if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) {
+				if (STATS) wc->tri_accepts++;
+				hit = idx;
+			}
+		}
+		if (hit >= 0) return hit;
+		prev = cur;
+		// NextPoint
+		float tn = 1000000.0f, s;
+		if (fabs((double)vx) > 1e-6) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
+		if (fabs((double)vy) > 1e-6) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
+		if (fabs((double)vz) > 1e-6) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
+		tn = (float)((double)tn + 0.1);
+		qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
+		t = tn;
+	}
+	return -1;
+}
+
+// ---- form factor ---------------------------------------------------------------------------------
+// One shooter sample point (the fields CalFF reads from its source triangle, shade.cpp:107-127).
+struct FFSample {
+	float cx, cy, cz;
+	float nx, ny, nz;
+	float area;
+	float nlen;	// norm(n): per-shot invariant, hoisted out of CalFF (same value, computed once)
+};
+
+struct FFCounters { unsigned calff, rays, visible; };
+
+// CalFF (shade.cpp:107-127).  desLen = norm(receiver normal) is passed in (pure function of n).
+template <bool STATS>
+RADK_HD float cal_ff(const DevTree &T, const FFSample &S, int logsrc, float ndx, float ndy, float ndz, float desLen,
+		     int logdest, float px, float py, float pz, FFCounters *fc, WalkCounters *wc) {
+	if (STATS) fc->calff++;
+	const float dx = S.cx - px, dy = S.cy - py, dz = S.cz - pz;
+	const float dotSrc = dot3(dx, dy, dz, S.nx, S.ny, S.nz);
+	const float dotDes = -dot3(dx, dy, dz, ndx, ndy, ndz);
+	if ((dotSrc < 0) != (dotDes < 0)) return 0.0f;
+	const float n2 = dx * dx + dy * dy + dz * dz;
+	const float dirLen = sqrtf(n2);
+	const float ct1 = dotSrc / dirLen / S.nlen;
+	const float ct2 = dotDes / dirLen / desLen;
+	float ff = ct1 * ct2;
+	if (ff <= 0.0f) return 0.0f;
+	ff = (float)((double)ff * ((double)S.area / ((double)n2 * 3.1415926535897932)));
+	if (ff <= 0.0f) return 0.0f;
+	if (STATS) fc->rays++;
+	if (ray_walk<STATS>(T, px, py, pz, dx, dy, dz, logdest, wc) == logsrc) {
+		if (STATS) fc->visible++;
+		return ff;
+	}
+	return 0.0f;
+}
+
+// What the loop needs to know about the current shooter; written once per shot by the selection
+// kernel (K1 + K2: listCanditate rad.cpp:387-404, AdaptCalFF's split shade.cpp:146-161,
+// PartitionSource shade.cpp:76-99) and read by every receiver thread.
+struct ShooterRec {
+	FFSample centre;	// the triangle itself (the sample whose result AdaptCalFF discards)
+	FFSample half[2];	// t1 = {m, p[e+2], p[e]}, t2 = {m, p[e+1], p[e+2]}
+	float dB[3];		// unshot radiosity being shot
+	float delta;		// (dB0+dB1)+dB2
+	int splittable;		// longest edge^2 >= 0.1 (shade.cpp:154)
+	int logsrc;		// original parent of the shooter = the index a visible ray must return
+	int slot;		// TriStore slot (global)
+	int recv;		// receiver index on the owning shard (-1 when owned by another rank)
+	int valid;		// 0: no candidate (converged)
+	int pad[3];
+};
+
+// K2: the shooter record of a receiver with vertices p, original normal n (|n| = nlen), area and
+// unshot energy dB (AdaptCalFF's longest-edge choice shade.cpp:146-156, PartitionSource 76-99).
+RADK_HD void make_shooter(const float p[3][3], float nx, float ny, float nz, float nlen, float area,
+			  float d0, float d1, float d2, int parent, int slot, int recv, ShooterRec *out) {
+	ShooterRec s;
+	s.centre.cx = (float)((double)(p[0][0] + p[1][0] + p[2][0]) / 3.0);	// CalCenter, vector.h:54-57
+	s.centre.cy = (float)((double)(p[0][1] + p[1][1] + p[2][1]) / 3.0);
+	s.centre.cz = (float)((double)(p[0][2] + p[1][2] + p[2][2]) / 3.0);
+	s.centre.nx = nx, s.centre.ny = ny, s.centre.nz = nz, s.centre.nlen = nlen;
+	s.centre.area = area;
+	int e = 0;
+	float maxlen = 0.0f;
+	for (int v = 0; v < 3; v++) {	// first maximum wins
+		const float *a = p[v], *b = p[(v + 1) % 3];
+		const float dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+		const float l = dx * dx + dy * dy + dz * dz;
+		if (maxlen < l) maxlen = l, e = v;
+	}
+	s.splittable = !((double)maxlen < 0.1);
+	const int i0 = e, i1 = (e + 1) % 3, i2 = (e + 2) % 3;
+	float m[3], c1[3], c2[3];
+	for (int k = 0; k < 3; k++) m[k] = (float)((double)(p[i0][k] + p[i1][k]) / 2.0);
+	for (int k = 0; k < 3; k++) {	// t1 = {m, p[i2], p[i0]}, t2 = {m, p[i1], p[i2]}
+		c1[k] = (float)((double)(m[k] + p[i2][k] + p[i0][k]) / 3.0);
+		c2[k] = (float)((double)(m[k] + p[i1][k] + p[i2][k]) / 3.0);
+	}
+	s.half[0] = s.centre, s.half[1] = s.centre;
+	s.half[0].cx = c1[0], s.half[0].cy = c1[1], s.half[0].cz = c1[2];
+	s.half[1].cx = c2[0], s.half[1].cy = c2[1], s.half[1].cz = c2[2];
+	s.half[0].area = s.half[1].area = (float)((double)area / 2.0);
+	s.dB[0] = d0, s.dB[1] = d1, s.dB[2] = d2;
+	s.delta = d0 + d1 + d2;
+	s.logsrc = parent;
+	s.slot = slot;
+	s.recv = recv;
+	s.valid = 1;
+	s.pad[0] = s.pad[1] = s.pad[2] = 0;
+	*out = s;
+}
+
+// AdaptCalFF(CalFF(centre)) as it executes (shade.cpp:141-168, stray ';' at 164): for a splittable
+// shooter the value is CalFF(t1)+CalFF(t2); the centre sample only matters for the statistics.
+template <bool STATS>
+RADK_HD float adapt_ff(const DevTree &T, const ShooterRec &sh, float ndx, float ndy, float ndz, float desLen,
+		       int logdest, float px, float py, float pz, FFCounters *fc, WalkCounters *wc) {
+	if (!sh.splittable)
+		return cal_ff<STATS>(T, sh.centre, sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
+	if (STATS) {	// reference-equivalent counting of the discarded centre sample (no walk needed)
+		fc->calff++;
+		const float dx = sh.centre.cx - px, dy = sh.centre.cy - py, dz = sh.centre.cz - pz;
+		const float dotSrc = dot3(dx, dy, dz, sh.centre.nx, sh.centre.ny, sh.centre.nz);
+		const float dotDes = -dot3(dx, dy, dz, ndx, ndy, ndz);
+		if ((dotSrc < 0) == (dotDes < 0)) {
+			const float n2 = dx * dx + dy * dy + dz * dz;
+			const float dirLen = sqrtf(n2);
+			float ff = (dotSrc / dirLen / sh.centre.nlen) * (dotDes / dirLen / desLen);
+			if (!(ff <= 0.0f)) {
+				ff = (float)((double)ff * ((double)sh.centre.area / ((double)n2 * 3.1415926535897932)));
+				if (!(ff <= 0.0f)) {
+					fc->rays++;
+					// its visibility is the same walk the reference does; trace it only for the count
+					if (ray_walk<false>(T, px, py, pz, dx, dy, dz, logdest, nullptr) == sh.logsrc) fc->visible++;
+				}
+			}
+		}
+	}
+	const float f1 = cal_ff<STATS>(T, sh.half[0], sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
+	const float f2 = cal_ff<STATS>(T, sh.half[1], sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
+	return f1 + f2;
+}
+
+}  // namespace radk

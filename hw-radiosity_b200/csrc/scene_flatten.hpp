@@ -1,0 +1,223 @@
+// Host-side flattening of a scene into the arrays the kernels read (pure C++, no CUDA calls):
+//  * the octree becomes a dense cell->leaf table + per-node float4 records + the leaf lists,
+//  * occluders TriStore[0..n0) become 5 float4 each,
+//  * receivers (slots with parent >= 0) are sorted by (original parent, Morton code), sharded by
+//    rank, and split into float4 planes; vertices shared by receivers of one original are merged.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "radk.h"
+#include "rt_core.cuh"
+
+namespace radk {
+
+struct FlatScene {
+	// octree
+	std::vector<int> cell_leaf;
+	std::vector<float4> leaf_lo, leaf_hi;
+	std::vector<int> list;
+	std::vector<float4> occ;
+	// receivers of this shard
+	int R = 0, U = 0, leaves_total = 0;
+	std::vector<int> recv_slot, recv_parent;
+	std::vector<float4> geo[3], st[3];
+	std::vector<int> slot_to_recv;
+	std::vector<float4> par_n, par_fk;
+	std::vector<int4> vid;
+	std::vector<float4> uv;
+	std::string error;
+
+	DevTree host_tree(const radk_scene *s) const {	// the same view the kernels get, over host memory
+		DevTree T;
+		T.cell_leaf = cell_leaf.data(), T.leaf_lo = leaf_lo.data(), T.leaf_hi = leaf_hi.data();
+		T.list = list.data(), T.occ = occ.data();
+		for (int k = 0; k < 3; k++) T.G0[k] = s->G0[k], T.G1[k] = s->G1[k];
+		T.min_grid_len = s->min_grid_len, T.grid_num = s->grid_num;
+		return T;
+	}
+};
+
+namespace flat_detail {
+inline uint32_t spread3(uint32_t x) {	// 10 bits -> every third bit
+	x &= 0x3ff;
+	x = (x | (x << 16)) & 0x030000ff;
+	x = (x | (x << 8)) & 0x0300f00f;
+	x = (x | (x << 4)) & 0x030c30c3;
+	x = (x | (x << 2)) & 0x09249249;
+	return x;
+}
+struct VKey {
+	uint32_t x, y, z;
+	int parent;
+	bool operator==(const VKey &o) const { return x == o.x && y == o.y && z == o.z && parent == o.parent; }
+};
+struct VKeyHash {
+	size_t operator()(const VKey &k) const {
+		uint64_t h = k.x * 0x9E3779B97F4A7C15ull;
+		h ^= (h >> 29) + k.y * 0xBF58476D1CE4E5B9ull;
+		h ^= (h >> 31) + k.z * 0x94D049BB133111EBull;
+		h ^= (h >> 27) + (uint32_t)k.parent * 0xD6E8FEB86659FD93ull;
+		return (size_t)(h ^ (h >> 32));
+	}
+};
+inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float ibits(int i) { float f; memcpy(&f, &i, 4); return f; }
+inline float4 f4(float a, float b, float c, float d) { float4 r; r.x = a, r.y = b, r.z = c, r.w = d; return r; }
+inline int4 i4(int a, int b, int c, int d) { int4 r; r.x = a, r.y = b, r.z = c, r.w = d; return r; }
+}  // namespace flat_detail
+
+// Returns a RADK_* code; on failure F.error holds the message.
+inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F) {
+	using namespace flat_detail;
+	// ---- octree: dense cell table by running the reference descent (raycast.cpp:266-278) per cell
+	const int g = s->grid_num, dim = g + 1;
+	if (g <= 0 || (long long)dim * dim * dim > (1ll << 28)) { F.error = "grid_num out of range"; return RADK_ERR_ARG; }
+	if (s->nnodes <= 0) { F.error = "empty octree"; return RADK_ERR_ARG; }
+	std::vector<int> depth(s->nnodes, 0);
+	F.cell_leaf.assign((size_t)dim * dim * dim, 0);
+	for (int z = 0; z < dim; z++)
+		for (int y = 0; y < dim; y++)
+			for (int x = 0; x < dim; x++) {
+				int gn[3] = {x, y, z}, node = 0, gsize = g, d = 0;
+				while (s->nodes[node].list < 0) {
+					gsize >>= 1;
+					int idx = 0;
+					for (int i = 0; i < 3; i++)
+						if (gn[i] >= gsize) idx |= 1 << i, gn[i] -= gsize;
+					node = s->nodes[node].sub[idx];
+					d++;
+					if (node < 0 || node >= s->nnodes || d > 64) { F.error = "malformed octree"; return RADK_ERR_ARG; }
+				}
+				depth[node] = d;
+				F.cell_leaf[((size_t)z * dim + y) * dim + x] = node;
+			}
+	F.leaf_lo.resize(s->nnodes), F.leaf_hi.resize(s->nnodes);
+	for (int i = 0; i < s->nnodes; i++) {
+		const radk_tree_node &nd = s->nodes[i];
+		F.leaf_lo[i] = f4(nd.g0[0], nd.g0[1], nd.g0[2], ibits(nd.list));
+		F.leaf_hi[i] = f4(nd.g1[0], nd.g1[1], nd.g1[2], ibits(depth[i]));
+	}
+	F.list.assign(s->list, s->list + s->nlist);
+	F.occ.resize((size_t)s->n0 * OCC_STRIDE);
+	for (int i = 0; i < s->n0; i++) {
+		const radk_triangle &t = s->tri[i];
+		float4 *q = &F.occ[(size_t)i * OCC_STRIDE];
+		q[0] = f4(t.n[0], t.n[1], t.n[2], t.c[0]);
+		q[1] = f4(t.c[1], t.c[2], t.se[0][0], t.se[0][1]);
+		q[2] = f4(t.se[0][2], t.se[0][3], t.se[1][0], t.se[1][1]);
+		q[3] = f4(t.se[1][2], t.se[1][3], t.se[2][0], t.se[2][1]);
+		q[4] = f4(t.se[2][2], t.se[2][3], 0.f, 0.f);
+	}
+
+	// ---- receivers: leaves sorted by (parent, Morton code of the centroid), then sharded
+	std::vector<int> leaves;
+	leaves.reserve(s->trinum / 2 + 1);
+	for (int i = 0; i < s->trinum; i++)
+		if (s->tri[i].parent >= 0) {
+			if (s->tri[i].parent >= s->n0) { F.error = "parent index outside the input triangles"; return RADK_ERR_ARG; }
+			leaves.push_back(i);
+		}
+	const float ext = s->G1[0] - s->G0[0];
+	auto morton = [&](const float *p) {
+		uint32_t q[3];
+		for (int k = 0; k < 3; k++) {
+			float f = ext > 0 ? (p[k] - s->G0[k]) / ext : 0.f;
+			f = f < 0.f ? 0.f : (f > 1.f ? 1.f : f);
+			q[k] = (uint32_t)(f * 1023.0f);
+		}
+		return spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+	};
+	std::vector<uint64_t> lkey(leaves.size());
+	for (size_t i = 0; i < leaves.size(); i++) {
+		const radk_triangle &t = s->tri[leaves[i]];
+		const float cen[3] = {(t.p[0][0] + t.p[1][0] + t.p[2][0]) / 3, (t.p[0][1] + t.p[1][1] + t.p[2][1]) / 3,
+				      (t.p[0][2] + t.p[1][2] + t.p[2][2]) / 3};
+		lkey[i] = ((uint64_t)(uint32_t)t.parent << 32) | morton(cen);
+	}
+	std::vector<int> order(leaves.size());
+	std::iota(order.begin(), order.end(), 0);
+	std::sort(order.begin(), order.end(), [&](int a, int b) { return lkey[a] != lkey[b] ? lkey[a] < lkey[b] : leaves[a] < leaves[b]; });
+	F.leaves_total = (int)leaves.size();
+	if (world < 1) world = 1;
+	const long long L = (long long)leaves.size();
+	const int lo_i = (int)(L * rank / world), hi_i = (int)(L * (rank + 1) / world);
+	const int R = hi_i - lo_i;
+	F.R = R;
+	F.recv_slot.resize(R);
+	F.recv_parent.resize(R);
+	for (int v = 0; v < 3; v++) F.geo[v].resize(R), F.st[v].resize(R);
+	F.slot_to_recv.assign(s->trinum, -1);
+	F.par_n.assign(s->n0, f4(0, 0, 0, 0));
+	F.par_fk.assign(s->n0, f4(0, 0, 0, 0));
+	// per-original tables cover every original (also those whose receivers live on other ranks):
+	// a shooter owned elsewhere still needs its normal here.
+	std::vector<char> par_seen(s->n0, 0);
+	const float kref = (float)(0.5 / 255.0);	// shade.cpp:246
+	for (size_t i = 0; i < leaves.size(); i++) {
+		const radk_triangle &t = s->tri[leaves[i]];
+		const float nlen = sqrtf(t.n[0] * t.n[0] + t.n[1] * t.n[1] + t.n[2] * t.n[2]);
+		const float4 pn = f4(t.n[0], t.n[1], t.n[2], nlen);
+		const float4 fk = f4(t.Frgb[0] * kref, t.Frgb[1] * kref, t.Frgb[2] * kref, 0.f);
+		if (!par_seen[t.parent]) {
+			par_seen[t.parent] = 1, F.par_n[t.parent] = pn, F.par_fk[t.parent] = fk;
+		} else if (memcmp(&F.par_n[t.parent], &pn, 12) != 0 || memcmp(&F.par_fk[t.parent], &fk, 12) != 0) {
+			F.error = "receivers of one original disagree on normal/reflectance: not a mesh produced by PrePartitionTriangles";
+			return RADK_ERR_STATE;
+		}
+	}
+	for (int r = 0; r < R; r++) {
+		const int slot = leaves[order[lo_i + r]];
+		const radk_triangle &t = s->tri[slot];
+		F.recv_slot[r] = slot;
+		F.recv_parent[r] = t.parent;
+		F.slot_to_recv[slot] = r;
+		F.geo[0][r] = f4(t.p[0][0], t.p[0][1], t.p[0][2], ibits(t.parent));
+		F.geo[1][r] = f4(t.p[1][0], t.p[1][1], t.p[1][2], ibits(slot));
+		F.geo[2][r] = f4(t.p[2][0], t.p[2][1], t.p[2][2], t.area);
+		for (int v = 0; v < 3; v++) F.st[v][r] = f4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
+	}
+
+	// ---- unique (vertex, parent) pairs of this shard, sorted by (parent, Morton)
+	std::unordered_map<VKey, int, VKeyHash> seen;
+	seen.reserve((size_t)R * 2);
+	std::vector<VKey> ukeys;
+	std::vector<float4> upos;
+	F.vid.resize(R);
+	for (int r = 0; r < R; r++) {
+		int ids[3];
+		for (int v = 0; v < 3; v++) {
+			const float4 &gp = F.geo[v][r];
+			// exact bit patterns: p enters the arithmetic by value, so -0/+0 are not merged
+			const VKey k{fbits(gp.x), fbits(gp.y), fbits(gp.z), F.recv_parent[r]};
+			auto it = seen.find(k);
+			if (it == seen.end()) {
+				it = seen.emplace(k, (int)ukeys.size()).first;
+				ukeys.push_back(k);
+				upos.push_back(f4(gp.x, gp.y, gp.z, ibits(F.recv_parent[r])));
+			}
+			ids[v] = it->second;
+		}
+		F.vid[r] = i4(ids[0], ids[1], ids[2], F.recv_parent[r]);
+	}
+	const int U = (int)ukeys.size();
+	F.U = U;
+	std::vector<uint64_t> ukey2(U);
+	for (int u = 0; u < U; u++) {
+		const float p[3] = {upos[u].x, upos[u].y, upos[u].z};
+		ukey2[u] = ((uint64_t)(uint32_t)ukeys[u].parent << 32) | morton(p);
+	}
+	std::vector<int> uorder(U), unew(U);
+	std::iota(uorder.begin(), uorder.end(), 0);
+	std::sort(uorder.begin(), uorder.end(), [&](int a, int b) { return ukey2[a] != ukey2[b] ? ukey2[a] < ukey2[b] : a < b; });
+	F.uv.resize(U);
+	for (int i = 0; i < U; i++) unew[uorder[i]] = i, F.uv[i] = upos[uorder[i]];
+	for (int r = 0; r < R; r++) F.vid[r] = i4(unew[F.vid[r].x], unew[F.vid[r].y], unew[F.vid[r].z], F.vid[r].w);
+	return RADK_OK;
+}
+
+}  // namespace radk

@@ -154,6 +154,10 @@ void radk_ctx_destroy(radk_ctx *c);
 /* Re-upload radiosity state (accB, deltaB) from the scene's slots; geometry unchanged. */
 int radk_ctx_reset(radk_ctx *c, const radk_scene *s);
 
+/* Restore the radiosity state of the last create/reset from its device-resident copy (no host
+ * traffic); used to re-run the same scene. */
+int radk_ctx_rewind(radk_ctx *c);
+
 /* Runs up to max_shots iterations of parallelRadiosity() (rad.cpp:406-451) on the device.
  * *converged = 1 when listCanditate() came back empty (that iteration is not counted as a shot).
  * max_shots < 0: run to convergence. */
@@ -177,6 +181,12 @@ int radk_ctx_snapshot_colors(radk_ctx *c, int *rgb, int trinum);
 int radk_ctx_stats(radk_ctx *c, radk_stats *st);
 /* Device time (ms, CUDA events on the context's stream) spent inside radk_ctx_step so far. */
 double radk_ctx_device_ms(const radk_ctx *c);
+/* Profiling aid: runs up to nshots single-source shots with a CUDA-event pair around every kernel
+ * launch and returns the average device time (ms) per launch of K3a (vertex_ff_kernel) and K3b
+ * (update_select_kernel), and the number of shots actually run. */
+int radk_ctx_kernel_times(radk_ctx *c, int nshots, double *k3a_ms, double *k3b_ms, int *shots_run);
+/* Sizes of this context's shard: receivers, unique vertices, occluders, octree nodes. */
+int radk_ctx_sizes(const radk_ctx *c, int *receivers, int *unique_vertices, int *occluders, int *nodes);
 
 /* Batch RayHitted (raycast.cpp:335-360): n rays (p[n][3], v[n][3], from[n]) -> hit[n]. */
 int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from, int n, int *hit);

@@ -1,0 +1,65 @@
+import gzip
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(GOLDEN_DIR, "golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def models_dir(tmp_path_factory):
+    """The reference's model/*.tri inputs, unpacked from tests/golden/models/*.tri.gz."""
+    d = tmp_path_factory.mktemp("models")
+    src = os.path.join(GOLDEN_DIR, "models")
+    for fn in os.listdir(src):
+        if fn.endswith(".tri.gz"):
+            with gzip.open(os.path.join(src, fn)) as f, open(d / fn[:-3], "wb") as g:
+                g.write(f.read())
+    return d
+
+
+@pytest.fixture(scope="session")
+def hr():
+    import hw_radiosity_b200 as mod
+    mod.load_library()
+    return mod
+
+
+@pytest.fixture(scope="session")
+def po():
+    from oracle import pyoracle
+    pyoracle.lib()
+    return pyoracle
+
+
+def oracle_scene(po, model, **kw):
+    """A CPU-oracle scene over a copy of the product front end's frozen mesh + octree."""
+    s = model.scene
+    return po.Scene(model.triangles.copy(), model.n0, model.nodes.copy(), model.tri_list.copy(), s.G0, s.G1,
+                    s.min_grid_len, s.grid_num, sample_area=model.sample_area, **kw)
+
+
+def state_digest(tri):
+    live = tri["parent"] >= 0
+    return {"trinum": len(tri), "leaves": int(live.sum()), "accB_sha": sha(tri["accB"][live]),
+            "deltaB_sha": sha(tri["deltaB"][live])}

@@ -1,0 +1,130 @@
+// TEST INFRASTRUCTURE - CPU emulation of the device code paths.
+//
+// Compiles hw-radiosity_b200/csrc/rt_core.cuh (the __host__ __device__ core: octree walk, triangle
+// test, form factor, shooter setup) and scene_flatten.hpp with plain g++ so that the logic the
+// kernels run can be checked against the oracle in the CPU-only test tier, before any GPU time is
+// spent.  It re-states the few lines of kernel glue (per-thread bodies of vertex_ff_kernel and
+// update_select_kernel) sequentially.  It is NOT part of the product and NOT a fallback: nothing
+// under hw-radiosity_b200/ references this file.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "radk.h"
+#include "rt_core.cuh"
+#include "scene_flatten.hpp"
+
+using namespace radk;
+
+namespace {
+inline unsigned ordered_bits(float f) {
+	unsigned u; memcpy(&u, &f, 4);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+}
+
+extern "C" {
+
+int emu_rays(const radk_scene *s, const float *p, const float *v, const int *from, int n, int *out) {
+	FlatScene F;
+	if (flatten_scene(s, 0, 1, F)) { fprintf(stderr, "emu: %s\n", F.error.c_str()); return 1; }
+	const DevTree T = F.host_tree(s);
+	for (int i = 0; i < n; i++)
+		out[i] = ray_walk<false>(T, p[3 * i], p[3 * i + 1], p[3 * i + 2], v[3 * i], v[3 * i + 1], v[3 * i + 2], from[i], nullptr);
+	return 0;
+}
+
+// Runs `shots` single-source shots the way the kernels do (unique-vertex form factors, then the
+// per-receiver update with the fused argmax) and writes accB[trinum][3][3], deltaB[trinum][3] and
+// the shooter slot of every shot.  counters[0..2] = reference-equivalent rays, visible, shaded receivers.
+int emu_run(const radk_scene *s, float converge, int rank, int world, int shots, float *accB, float *deltaB,
+	    int *shooters, int *nshots_out, long long *counters) {
+	FlatScene F;
+	if (flatten_scene(s, rank, world, F)) { fprintf(stderr, "emu: %s\n", F.error.c_str()); return 1; }
+	const DevTree T = F.host_tree(s);
+	const int R = F.R, U = F.U;
+	std::vector<float> ff0(U), ff1(U);
+	std::vector<unsigned> vstat(U);
+	auto select = [&](ShooterRec *out) {
+		unsigned long long best = 0;
+		for (int r = 0; r < R; r++) {
+			const float delta = F.st[0][r].w + F.st[1][r].w + F.st[2][r].w;
+			if (!(delta > converge)) continue;
+			const unsigned long long k = ((unsigned long long)ordered_bits(delta) << 32) | (unsigned)F.recv_slot[r];
+			best = k > best ? k : best;
+		}
+		if (!best) { out->valid = 0; return; }
+		const int r = F.slot_to_recv[(int)(best & 0xffffffffu)];
+		const float p[3][3] = {{F.geo[0][r].x, F.geo[0][r].y, F.geo[0][r].z}, {F.geo[1][r].x, F.geo[1][r].y, F.geo[1][r].z},
+				       {F.geo[2][r].x, F.geo[2][r].y, F.geo[2][r].z}};
+		const int parent = F.recv_parent[r];
+		const float4 pn = F.par_n[parent];
+		make_shooter(p, pn.x, pn.y, pn.z, pn.w, F.geo[2][r].w, F.st[0][r].w, F.st[1][r].w, F.st[2][r].w, parent,
+			     F.recv_slot[r], r, out);
+	};
+	long long rays = 0, visible = 0, shaded = 0;
+	int done = 0;
+	ShooterRec sh;
+	select(&sh);
+	while (done < shots && sh.valid) {
+		for (int u = 0; u < U; u++) {	// vertex_ff_kernel
+			const float4 v = F.uv[u];
+			const int parent = float_as_int_hd(v.w);
+			const float4 pn = F.par_n[parent];
+			FFCounters fc = {0, 0, 0};
+			WalkCounters wc = {0, 0, 0, 0, 0, 0, 0};
+			if (sh.splittable) {
+				// reference-equivalent counting incl. the discarded centre sample
+				cal_ff<true>(T, sh.centre, sh.logsrc, pn.x, pn.y, pn.z, pn.w, parent, v.x, v.y, v.z, &fc, &wc);
+				ff0[u] = cal_ff<true>(T, sh.half[0], sh.logsrc, pn.x, pn.y, pn.z, pn.w, parent, v.x, v.y, v.z, &fc, &wc);
+				ff1[u] = cal_ff<true>(T, sh.half[1], sh.logsrc, pn.x, pn.y, pn.z, pn.w, parent, v.x, v.y, v.z, &fc, &wc);
+			} else {
+				ff0[u] = cal_ff<true>(T, sh.centre, sh.logsrc, pn.x, pn.y, pn.z, pn.w, parent, v.x, v.y, v.z, &fc, &wc);
+				ff1[u] = 0.0f;
+			}
+			vstat[u] = fc.rays | (fc.visible << 8);
+		}
+		for (int r = 0; r < R; r++) {	// update_select_kernel
+			float4 &a0 = F.st[0][r], &a1 = F.st[1][r], &a2 = F.st[2][r];
+			if (F.recv_slot[r] == sh.slot) { a0.w = a1.w = a2.w = 0.0f; continue; }
+			if (!(a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
+			      a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f)) continue;
+			shaded++;
+			const int4 id = F.vid[r];
+			const int ids[3] = {id.x, id.y, id.z};
+			float ff[3];
+			for (int v = 0; v < 3; v++) {
+				ff[v] = ff0[ids[v]] + ff1[ids[v]];
+				rays += vstat[ids[v]] & 0xff, visible += vstat[ids[v]] >> 8;
+			}
+			const float4 fk = F.par_fk[id.w];
+			const float lo[3] = {fk.x * sh.dB[0] / 3, fk.y * sh.dB[1] / 3, fk.z * sh.dB[2] / 3};
+			float dB[3] = {a0.w, a1.w, a2.w};
+			float4 *acc[3] = {&a0, &a1, &a2};
+			for (int v = 0; v < 3; v++) {
+				float d;
+				d = lo[0] * ff[v]; dB[0] += d; acc[v]->x += d;
+				d = lo[1] * ff[v]; dB[1] += d; acc[v]->y += d;
+				d = lo[2] * ff[v]; dB[2] += d; acc[v]->z += d;
+			}
+			a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
+		}
+		if (shooters) shooters[done] = sh.slot;
+		done++;
+		select(&sh);
+	}
+	for (int r = 0; r < R; r++) {
+		const int slot = F.recv_slot[r];
+		for (int v = 0; v < 3; v++) {
+			accB[slot * 9 + v * 3 + 0] = F.st[v][r].x;
+			accB[slot * 9 + v * 3 + 1] = F.st[v][r].y;
+			accB[slot * 9 + v * 3 + 2] = F.st[v][r].z;
+			deltaB[slot * 3 + v] = F.st[v][r].w;
+		}
+	}
+	if (nshots_out) *nshots_out = done;
+	if (counters) counters[0] = rays, counters[1] = visible, counters[2] = shaded, counters[3] = U, counters[4] = R;
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+"""CPU-tier check of the code the kernels run: rt_core.cuh (octree walk, triangle test, form factor,
+shooter setup) and scene_flatten.hpp (cell table, receiver sort, vertex sharing) compiled with g++
+by tests/hostemu and compared bit-for-bit with the oracle.  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, oracle_scene
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(ROOT, "tests", "hostemu", "hostemu.cpp")
+    so = os.path.join(ROOT, "tests", "hostemu", "libhostemu.so")
+    deps = [src] + [os.path.join(ROOT, "hw-radiosity_b200", "csrc", f) for f in ("rt_core.cuh", "scene_flatten.hpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "hw-radiosity_b200", "csrc"),
+                               src, "-o", so])
+    lib = C.CDLL(so)
+    lib.emu_run.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+    lib.emu_rays.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    return lib
+
+
+def run_emu(emu, m, shots, rank=0, world=1, converge=1200.0):
+    n = m.trinum
+    accB = np.zeros((n, 3, 3), np.float32)
+    dB = np.zeros((n, 3), np.float32)
+    sh = np.zeros(max(shots, 1), np.int32)
+    ns = C.c_int()
+    cnt = (C.c_longlong * 8)()
+    assert emu.emu_run(C.addressof(m.scene), converge, rank, world, shots, accB.ctypes.data, dB.ctypes.data,
+                       sh.ctypes.data, C.byref(ns), cnt) == 0
+    return accB, dB, list(sh[: ns.value]), list(cnt)
+
+
+@pytest.mark.parametrize("name,shots", [("box", 6), ("church", 6), ("blocks", 8), ("sbox", 40), ("model3s", 40)])
+def test_device_core_matches_oracle(hr, po, emu, models_dir, name, shots):
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    sc = oracle_scene(po, m)
+    seq = sc.run(shots)
+    accB, dB, sh, cnt = run_emu(emu, m, shots)
+    live = sc.slots["parent"] >= 0
+    assert sh == [s[0] for s in seq]
+    assert np.array_equal(accB[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
+    assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
+    st = sc.stats
+    assert cnt[:3] == [st["rays"], st["visible"], st["receivers"]]
+
+
+def test_ray_walk_matches_oracle_on_random_rays(hr, po, emu, models_dir):
+    m = hr.Model(str(models_dir / "church.tri"))
+    sc = oracle_scene(po, m)
+    rng = np.random.default_rng(7)
+    tri = m.triangles
+    leaves = np.nonzero(tri["parent"] >= 0)[0]
+    a, b = rng.choice(leaves, 20000), rng.choice(leaves, 20000)
+    p = tri["p"][a, rng.integers(0, 3, len(a))]
+    v = tri["c"][b] - p
+    frm = tri["parent"][a]
+    want = sc.ray_hitted(p, v, frm)
+    got = np.empty(len(p), np.int32)
+    pp, vv, ff = np.ascontiguousarray(p), np.ascontiguousarray(v), np.ascontiguousarray(frm)
+    assert emu.emu_rays(C.addressof(m.scene), pp.ctypes.data, vv.ctypes.data, ff.ctypes.data, len(p), got.ctypes.data) == 0
+    assert np.array_equal(got, want)
+    assert (want >= 0).mean() > 0.5
+
+
+def test_sharded_receivers_union_equals_single(hr, emu, models_dir):
+    """Each rank's shard, shot with the same global shooter sequence, reproduces its part of the
+    single-GPU result (the shooter here is found per shard, so compare only one shot)."""
+    m = hr.Model(str(models_dir / "sbox.tri"))
+    accB1, dB1, sh1, _ = run_emu(emu, m, 1)
+    # world=1 rank=0 again through the sharding path with world 2: shard 0 holds the light? use ranks' union of one shot
+    # when the (single) global shooter lives in shard r, that shard's result equals the global one on its receivers.
+    hit = 0
+    for rank in range(2):
+        accB, dB, sh, cnt = run_emu(emu, m, 1, rank=rank, world=2)
+        if sh == sh1:
+            touched = np.nonzero((accB != 0).any(axis=(1, 2)) | (dB != 0).any(axis=1))[0]
+            assert np.array_equal(accB[touched].view(np.uint32), accB1[touched].view(np.uint32))
+            hit += 1
+    assert hit >= 1
