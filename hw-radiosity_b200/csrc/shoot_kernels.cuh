@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128) vertex_ff_kernel(DevScene S, const Shoote
 	__shared__ ShooterRec sh;
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)shp)[threadIdx.x];
 	__syncthreads();
-	if (!sh.valid) return;
+	if (!sh.valid || *S.sel.converged) return;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	const int nthreads = sh.splittable ? 2 * S.U : S.U;
 	FFCounters fc = {0, 0, 0};
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) update_select_kernel(DevScene S, const Sh
 	__shared__ ShooterRec sh;
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)shp)[threadIdx.x];
 	__syncthreads();
-	if (!sh.valid) return;
+	if (!sh.valid || *S.sel.converged) return;
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long key = 0ull;
 	unsigned cand = 0u, shaded = 0u;
@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(256) update_select_kernel(DevScene S, const Sh
 	atomicAdd(&S.stats->shots, 1ull);
 	*S.sel.ncand = (int)total;
 	if (best == 0ull) {
+		// converged: no record may stay valid, later launches of the same batch must be no-ops
 		next->valid = 0;
+		const_cast<ShooterRec *>(shp)->valid = 0;
 		*S.sel.converged = 1;
 		return;
 	}
