@@ -211,7 +211,9 @@ def run_ours(args):
 
         # per-kernel durations, live, CUDA events on the launching stream (first shots of a fresh run)
         ctx.rewind()
-        kt = ctx.kernel_times(min(shots_per_step, 256))
+        flush.fill_(7)
+        torch.cuda.synchronize()
+        kt = ctx.profile(cap)
         ctx.rewind()
 
         # end-to-end through the C ABI with host buffers: state upload + loop + download
@@ -232,11 +234,15 @@ def run_ours(args):
         cpu = cpu_reference_run(tri, cpu_shots, threads)
 
     hbm_gbs, peak_src, sm_max = measured_peaks()
-    shot_ms = kt["k3a_ms"] + kt["k3b_ms"]
+    # dominant kernel: the visibility / form-factor kernel (K3a: ff_batch_kernel).  Algorithmic bytes per launch =
+    # 160 B x shaded receivers of the shots whose form factors the launch produced.
+    ff_ms, ff_n = kt["ms"]["form_factor"], max(kt["launches"]["form_factor"], 1)
+    upd_ms = kt["ms"]["update"]
     recv_per_shot = recv_shaded / max(shots_per_step, 1)
-    algo_bytes = ALGO_BYTES_PER_RECEIVER * recv_per_shot
-    dom = "vertex_ff_kernel (K3a)" if kt["k3a_ms"] >= kt["k3b_ms"] else "update_select_kernel (K3b)"
-    achieved = algo_bytes / (shot_ms * 1e-3) / 1e9 if shot_ms > 0 else 0.0
+    algo_bytes_per_step = ALGO_BYTES_PER_RECEIVER * recv_shaded
+    dom = "ff_batch_kernel (K3a: culls + form factor + octree walk)" if ff_ms >= upd_ms else "shots_kernel (K3b+K1)"
+    dom_ms = max(ff_ms, upd_ms)
+    achieved = algo_bytes_per_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # FP32 side of the SURVEY section 8(d) roofline, counted per traced ray by the device itself
     flops = (35 * walk["calff"] + 12 * walk["leaf_visits"] + 6 * walk["descent_steps"] + 22 * (walk["leaf_visits"] - walk["tri_accepts"] * 0)
              + 14 * walk["tri_tests"] + 24 * walk["tri_accepts"])
@@ -258,9 +264,14 @@ def run_ours(args):
                 "d2h_bytes_per_step": state_bytes, "seconds_per_step": e2e_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": None, "kernel": dom, "peak_source": peak_src,
-                     "note": "algorithmic bytes = 160 B x shaded receivers per shot over the K3a+K3b pair of one shot; "
-                             "church is FP32-issue/latency bound (SURVEY 8d), see fp32",
-                     "k3a_ms": kt["k3a_ms"], "k3b_ms": kt["k3b_ms"], "shots_profiled": kt["shots"]},
+                     "note": "achieved = 160 B x shaded receivers of the step / summed launch time of the dominant kernel "
+                             "(CUDA events per launch, profiled run); church is FP32-issue/latency bound, not HBM bound "
+                             "(SURVEY 8d): see fp32 and shot_roofline",
+                     "kernel_ms_per_step": kt["ms"], "kernel_launches_per_step": kt["launches"], "shots_profiled": kt["shots"]},
+        "shot_roofline": {"definition": "SURVEY 8(d): T_shot >= max(160 B x active receivers / HBM peak, counted FP32 ops / FP32 peak)",
+                          "bound_us_per_shot": max(ALGO_BYTES_PER_RECEIVER * recv_per_shot / (hbm_gbs * 1e9), flops / max(shots_per_step, 1) / p_fp32) * 1e6,
+                          "measured_us_per_shot": ms_per_step * 1e3 / max(shots_per_step, 1),
+                          "frac": max(ALGO_BYTES_PER_RECEIVER * recv_per_shot / (hbm_gbs * 1e9), flops / max(shots_per_step, 1) / p_fp32) / (ms_per_step * 1e-3 / max(shots_per_step, 1))},
         "fp32": {"flops_per_step_counted": flops, "achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
                  "peak_tflops": p_fp32 / 1e12, "frac": flops / (ms_per_step * 1e-3) / p_fp32},
         "cpu_baseline": {"value": cpu["rays"] / cpu["seconds"], "unit": "rays/s", "cores": threads, "kind": cpu["kind"],

@@ -39,7 +39,8 @@ class Opts(C.Structure):
     _fields_ = [("converge", C.c_float), ("parallel_src", C.c_int), ("tri_limit", C.c_int),
                 ("area_limit", C.c_float), ("sample_area", C.c_float), ("delta_ff", C.c_float),
                 ("max_tri", C.c_int), ("split_enabled", C.c_int), ("device", C.c_int), ("rank", C.c_int),
-                ("world", C.c_int), ("collect_stats", C.c_int), ("dedup", C.c_int), ("reserved", C.c_int * 6)]
+                ("world", C.c_int), ("collect_stats", C.c_int), ("dedup", C.c_int), ("per_shot_kernels", C.c_int),
+                ("ff_rows", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class ModelOpts(C.Structure):
@@ -64,7 +65,7 @@ EXPORTS = [
     "radk_model_write", "radk_model_format", "radk_ctx_create", "radk_ctx_destroy", "radk_ctx_reset",
     "radk_ctx_rewind", "radk_ctx_step", "radk_ctx_select", "radk_ctx_shoot", "radk_ctx_shooter_log", "radk_ctx_trinum",
     "radk_ctx_download", "radk_ctx_download_triangles", "radk_ctx_snapshot_colors", "radk_ctx_stats",
-    "radk_ctx_device_ms", "radk_ctx_kernel_times", "radk_ctx_sizes", "radk_ray_hitted", "radk_vertex_ff", "radk_ctx_local_candidate",
+    "radk_ctx_device_ms", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_vertex_ff", "radk_ctx_local_candidate",
     "radk_ctx_shoot_candidate", "radk_ctx_candidate_buffer", "radk_ctx_local_candidate_dev",
     "radk_ctx_shoot_gathered_dev", "radk_ctx_converged_flag",
 ]
@@ -116,7 +117,7 @@ def load_library():
     L.radk_ctx_destroy.restype = None
     L.radk_ctx_reset.argtypes = [vp, C.POINTER(SceneStruct)]
     L.radk_ctx_rewind.argtypes = [vp]
-    L.radk_ctx_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
+    L.radk_ctx_profile.argtypes = [vp, C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.radk_ctx_sizes.argtypes = [vp, ip, ip, ip, ip]
     L.radk_ctx_step.argtypes = [vp, C.c_longlong, C.POINTER(C.c_longlong), ip]
     L.radk_ctx_select.argtypes = [vp, ip, C.c_int, ip]
@@ -257,10 +258,12 @@ class Context:
         _check(load_library().radk_ctx_sizes(self._h, *[C.byref(x) for x in v]))
         return dict(zip(("receivers", "unique_vertices", "occluders", "nodes"), [x.value for x in v]))
 
-    def kernel_times(self, nshots):
-        a, b, n = C.c_double(), C.c_double(), C.c_int()
-        _check(load_library().radk_ctx_kernel_times(self._h, nshots, C.byref(a), C.byref(b), C.byref(n)))
-        return {"k3a_ms": a.value, "k3b_ms": b.value, "shots": n.value}
+    def profile(self, max_shots=-1):
+        """Per-kernel-class device time (CUDA events on the context's stream) over a run."""
+        ms, n, shots = (C.c_double * 3)(), (C.c_longlong * 3)(), C.c_longlong()
+        _check(load_library().radk_ctx_profile(self._h, max_shots, ms, n, C.byref(shots)))
+        names = ("select", "form_factor", "update")
+        return {"shots": shots.value, "ms": dict(zip(names, list(ms))), "launches": dict(zip(names, list(n)))}
 
     def step(self, max_shots=-1):
         done, conv = C.c_longlong(), C.c_int()

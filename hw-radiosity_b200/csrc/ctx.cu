@@ -15,6 +15,7 @@
 
 #include "radk.h"
 #include "shoot_kernels.cuh"
+#include "fast_kernels.cuh"
 #include "scene_flatten.hpp"
 
 namespace radk {
@@ -77,6 +78,19 @@ struct radk_ctx {
 	DevBuf<DevStats> stats;
 	DevBuf<ShooterRec> rec;			// [0],[1]: ping-pong for the single-source loop; [2..]: multi-source list
 	DevBuf<radk_candidate> cand;		// multi-GPU exchange buffer [world]
+	// fast path (fast_kernels.cuh)
+	DevBuf<float2> ffcache;
+	DevBuf<int> row_slot, slot_row, todo, fast_ints;	// fast_ints: [0]=ntodo [1]=stalled
+	DevBuf<ShooterRec> row_rec;
+	DevBuf<unsigned long long> group_key;
+	DevBuf<unsigned> fast_uints;			// [0]=ticket [1]=barrier
+	DevBuf<ShotRec> handoff;
+	DevBuf<Partial> partial;
+	DevBuf<long long> budget;
+	FastState F{};
+	bool use_fast = false;
+	int rows = 0, shots_ctas = 0;
+	long long *h_budget = nullptr;		// pinned
 	int max_blocks = 0;
 	int cur = 0;				// which of rec[0]/rec[1] holds the current shooter
 	bool have_current = false;		// rec[cur] is up to date with the device state
@@ -90,6 +104,39 @@ namespace {
 
 const int kShotLogCap = 1 << 20;
 const int kBatchShots = 32;
+
+int reset_fast_state(radk_ctx *c) {
+	if (!c->use_fast) return RADK_OK;
+	cudaStream_t st = c->stream;
+	CUDA_TRY(cudaMemsetAsync(c->row_slot.p, 0xff, kMaxRows * sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(c->slot_row.p, 0xff, std::max(c->trinum, 1) * sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(c->todo.p, 0, kMaxRows * sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(c->fast_ints.p, 0, 4 * sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(c->group_key.p, 0, kPredictGroups * sizeof(unsigned long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->fast_uints.p, 0, 4 * sizeof(unsigned), st));
+	CUDA_TRY(cudaMemsetAsync(c->handoff.p, 0, sizeof(ShotRec), st));
+	CUDA_TRY(cudaMemsetAsync(c->budget.p, 0, sizeof(long long), st));
+	return RADK_OK;
+}
+
+// One round of the fast path: predict -> batched form factors -> persistent shot loop.
+// ev (optional): 4 events recorded around the three kernels, for profiling.
+int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
+	cudaStream_t st = c->stream;
+	CUDA_TRY(cudaMemsetAsync(c->F.barrier, 0, sizeof(unsigned), st));
+	if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
+	predict_kernel<<<64, 1024, 0, st>>>(c->S, c->F);
+	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
+	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
+	ff_batch_kernel<<<g, kFFBlock, 0, st>>>(c->S, c->F);
+	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
+	int max_ctas = c->shots_ctas;
+	void *args[] = {(void *)&c->S, (void *)&c->F, (void *)&max_ctas};
+	CUDA_TRY(cudaLaunchCooperativeKernel((const void *)shots_kernel, dim3((unsigned)c->shots_ctas), dim3(kShotsBlock), args, 0, st));
+	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
+	c->launches += 3;
+	return RADK_OK;
+}
 
 int upload_scene(radk_ctx *c, const radk_scene *s) {
 	const radk_opts &o = c->opt;
@@ -137,6 +184,39 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(c->stats.alloc(1));
 	CUDA_TRY(c->rec.alloc(2 + kMaxSources));
 	CUDA_TRY(c->cand.alloc(world));
+	c->use_fast = c->use_dedup && !o.collect_stats && world == 1 && !o.per_shot_kernels;
+	if (c->use_fast) {
+		// form-factor cache rows: 32 unless that would take more than a quarter of the free memory
+		size_t free_b = 0, total_b = 0;
+		CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+		int rows = o.ff_rows > 0 ? std::min(o.ff_rows, kMaxRows) : 32;
+		while (rows > 2 && (size_t)rows * std::max(U, 1) * sizeof(float2) > free_b / 4) rows >>= 1;
+		c->rows = rows;
+		int dev_sms = 0, per_sm = 0;
+		CUDA_TRY(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device));
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shots_kernel, kShotsBlock, 0));
+		per_sm = std::max(1, std::min(per_sm, 2));
+		// no more CTAs than there is work for (a CTA needs a few receivers per thread to be worth a barrier slot)
+		c->shots_ctas = std::max(1, std::min(dev_sms * per_sm, (R + kShotsBlock - 1) / kShotsBlock));
+		CUDA_TRY(c->ffcache.alloc((size_t)rows * std::max(U, 1)));
+		CUDA_TRY(c->row_slot.alloc(kMaxRows));
+		CUDA_TRY(c->slot_row.alloc(std::max(s->trinum, 1)));
+		CUDA_TRY(c->todo.alloc(kMaxRows));
+		CUDA_TRY(c->fast_ints.alloc(4));
+		CUDA_TRY(c->row_rec.alloc(kMaxRows));
+		CUDA_TRY(c->group_key.alloc(kPredictGroups));
+		CUDA_TRY(c->fast_uints.alloc(4));
+		CUDA_TRY(c->handoff.alloc(1));
+		CUDA_TRY(c->partial.alloc(2 * (size_t)c->shots_ctas));
+		CUDA_TRY(c->budget.alloc(1));
+		FastState &F = c->F;
+		F.ff = c->ffcache.p, F.rows = rows, F.row_slot = c->row_slot.p, F.slot_row = c->slot_row.p;
+		F.rec = c->row_rec.p, F.todo = c->todo.p, F.ntodo = c->fast_ints.p, F.stalled = c->fast_ints.p + 1;
+		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.barrier = c->fast_uints.p + 1;
+		F.handoff = c->handoff.p, F.partial = c->partial.p, F.budget = c->budget.p;
+		int rc2 = reset_fast_state(c);
+		if (rc2) return rc2;
+	}
 	CUDA_TRY(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned), st));
 	CUDA_TRY(cudaMemsetAsync(c->bound.p, 0xff, sizeof(unsigned long long), st));
 	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), st));
@@ -154,6 +234,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	for (int k = 0; k < 3; k++) S.tree.G0[k] = s->G0[k], S.tree.G1[k] = s->G1[k];
 	S.tree.min_grid_len = s->min_grid_len;
 	S.tree.grid_num = s->grid_num;
+	S.tree.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
 	S.R = R, S.U = U, S.n0 = s->n0;
 	for (int v = 0; v < 3; v++) S.geo[v] = c->geo[v].p, S.st[v] = c->st[v].p;
 	S.vid = c->vid.p, S.slot = c->slot.p, S.uv = c->uv.p, S.ffh = c->ffh.p, S.vstat = c->vstat.p;
@@ -208,6 +289,7 @@ void launch_multi_source_iteration(radk_ctx *c) {
 int read_flags(radk_ctx *c) {
 	CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags.p, sizeof(*c->h_flags), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(c->h_shots, c->shots_done.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+	if (c->use_fast) CUDA_TRY(cudaMemcpyAsync(c->h_budget, c->budget.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return RADK_OK;
 }
@@ -239,7 +321,8 @@ int radk_ctx_create(const radk_scene *s, const radk_opts *o, radk_ctx **out) {
 		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 		    cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
 		    cudaMallocHost((void **)&c->h_flags, sizeof(*c->h_flags)) != cudaSuccess ||
-		    cudaMallocHost((void **)&c->h_shots, sizeof(long long)) != cudaSuccess) {
+		    cudaMallocHost((void **)&c->h_shots, sizeof(long long)) != cudaSuccess ||
+		    cudaMallocHost((void **)&c->h_budget, sizeof(long long)) != cudaSuccess) {
 			set_error(std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()));
 			rc = RADK_ERR_CUDA;
 			break;
@@ -257,6 +340,7 @@ void radk_ctx_destroy(radk_ctx *c) {
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->h_flags) cudaFreeHost(c->h_flags);
 	if (c->h_shots) cudaFreeHost(c->h_shots);
+	if (c->h_budget) cudaFreeHost(c->h_budget);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -280,6 +364,7 @@ int radk_ctx_reset(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->stats.p, 0, sizeof(DevStats), c->stream));
+	{ int rc2 = reset_fast_state(c); if (rc2) return rc2; }
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->have_current = false;
 	c->device_ms = 0;
@@ -293,6 +378,7 @@ int radk_ctx_rewind(radk_ctx *c) {
 		CUDA_TRY(cudaMemcpyAsync(c->st[v].p, c->st0[v].p, (size_t)c->R * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), c->stream));
+	{ int rc2 = reset_fast_state(c); if (rc2) return rc2; }	// cached form factors are dropped: a re-run recomputes everything
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->have_current = false;
 	return RADK_OK;
@@ -307,42 +393,67 @@ int radk_ctx_sizes(const radk_ctx *c, int *receivers, int *unique_vertices, int 
 	return RADK_OK;
 }
 
-int radk_ctx_kernel_times(radk_ctx *c, int nshots, double *k3a_ms, double *k3b_ms, int *shots_run) {
-	if (!c || nshots <= 0) { set_error("radk_ctx_kernel_times: bad argument"); return RADK_ERR_ARG; }
-	if (!c->use_dedup) { set_error("radk_ctx_kernel_times: single-source contexts only"); return RADK_ERR_STATE; }
+int radk_ctx_profile(radk_ctx *c, long long max_shots, double ms[3], long long n[3], long long *shots) {
+	if (!c || !ms || !n) { set_error("radk_ctx_profile: bad argument"); return RADK_ERR_ARG; }
+	if (!c->use_dedup) { set_error("radk_ctx_profile: single-source contexts only"); return RADK_ERR_STATE; }
 	CUDA_TRY(cudaSetDevice(c->device));
 	int rc = read_flags(c);
 	if (rc) return rc;
 	const long long before = *c->h_shots;
-	if (!c->have_current) { launch_select(c, c->rec.p + c->cur, 0); c->have_current = true; }
-	std::vector<cudaEvent_t> ev((size_t)nshots * 3);
+	for (int k = 0; k < 3; k++) ms[k] = 0, n[k] = 0;
+	cudaEvent_t ev[4];
 	for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
 	const bool stats = c->opt.collect_stats != 0;
-	for (int i = 0; i < nshots; i++) {
-		ShooterRec *cur = c->rec.p + c->cur, *nxt = c->rec.p + (c->cur ^ 1);
-		CUDA_TRY(cudaEventRecord(ev[3 * i], c->stream));
-		if (stats) vertex_ff_kernel<true><<<blocks_for(2 * c->U, 128), 128, 0, c->stream>>>(c->S, cur);
-		else vertex_ff_kernel<false><<<blocks_for(2 * c->U, 128), 128, 0, c->stream>>>(c->S, cur);
-		CUDA_TRY(cudaEventRecord(ev[3 * i + 1], c->stream));
-		if (stats) update_select_kernel<true><<<blocks_for(c->R, 256), 256, 0, c->stream>>>(c->S, cur, nxt);
-		else update_select_kernel<false><<<blocks_for(c->R, 256), 256, 0, c->stream>>>(c->S, cur, nxt);
-		CUDA_TRY(cudaEventRecord(ev[3 * i + 2], c->stream));
-		c->cur ^= 1;
-		c->launches += 2;
-	}
-	if ((rc = read_flags(c))) return rc;
-	const int ran = (int)(*c->h_shots - before);
-	double a = 0, b = 0;
-	for (int i = 0; i < ran; i++) {
-		float m1 = 0, m2 = 0;
-		CUDA_TRY(cudaEventElapsedTime(&m1, ev[3 * i], ev[3 * i + 1]));
-		CUDA_TRY(cudaEventElapsedTime(&m2, ev[3 * i + 1], ev[3 * i + 2]));
-		a += m1, b += m2;
+	long long done = 0;
+	if (c->use_fast) {
+		*c->h_budget = max_shots < 0 ? (1ll << 60) : max_shots;
+		CUDA_TRY(cudaMemcpyAsync(c->budget.p, c->h_budget, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+		while (true) {
+			if ((rc = launch_fast_round(c, ev))) return rc;
+			if ((rc = read_flags(c))) return rc;
+			for (int k = 0; k < 3; k++) {
+				float t = 0;
+				CUDA_TRY(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+				ms[k] += t, n[k]++;
+			}
+			done = *c->h_shots - before;
+			if (c->h_flags->converged || *c->h_budget <= 0) break;
+		}
+	} else {
+		if (!c->have_current) {
+			CUDA_TRY(cudaEventRecord(ev[0], c->stream));
+			launch_select(c, c->rec.p + c->cur, 0);
+			CUDA_TRY(cudaEventRecord(ev[1], c->stream));
+			CUDA_TRY(cudaEventSynchronize(ev[1]));
+			float t = 0;
+			CUDA_TRY(cudaEventElapsedTime(&t, ev[0], ev[1]));
+			ms[0] += t, n[0]++;
+			c->have_current = true;
+		}
+		while (max_shots < 0 || done < max_shots) {
+			ShooterRec *cur = c->rec.p + c->cur, *nxt = c->rec.p + (c->cur ^ 1);
+			CUDA_TRY(cudaEventRecord(ev[0], c->stream));
+			if (stats) vertex_ff_kernel<true><<<blocks_for(2 * c->U, 128), 128, 0, c->stream>>>(c->S, cur);
+			else vertex_ff_kernel<false><<<blocks_for(2 * c->U, 128), 128, 0, c->stream>>>(c->S, cur);
+			CUDA_TRY(cudaEventRecord(ev[1], c->stream));
+			if (stats) update_select_kernel<true><<<blocks_for(c->R, 256), 256, 0, c->stream>>>(c->S, cur, nxt);
+			else update_select_kernel<false><<<blocks_for(c->R, 256), 256, 0, c->stream>>>(c->S, cur, nxt);
+			CUDA_TRY(cudaEventRecord(ev[2], c->stream));
+			c->cur ^= 1;
+			c->launches += 2;
+			if ((rc = read_flags(c))) return rc;
+			if (*c->h_shots - before == done) break;	// nothing ran: converged
+			done = *c->h_shots - before;
+			float t1 = 0, t2 = 0;
+			CUDA_TRY(cudaEventElapsedTime(&t1, ev[0], ev[1]));
+			CUDA_TRY(cudaEventElapsedTime(&t2, ev[1], ev[2]));
+			ms[1] += t1, n[1]++, ms[2] += t2, n[2]++;
+			if (c->h_flags->converged) break;
+		}
 	}
 	for (auto &e : ev) cudaEventDestroy(e);
-	if (k3a_ms) *k3a_ms = ran ? a / ran : 0;
-	if (k3b_ms) *k3b_ms = ran ? b / ran : 0;
-	if (shots_run) *shots_run = ran;
+	if (shots) *shots = done;
+	CUDA_TRY(cudaGetLastError());
 	return RADK_OK;
 }
 
@@ -356,7 +467,23 @@ int radk_ctx_step(radk_ctx *c, long long max_shots, long long *shots_done, int *
 	long long done = 0;
 	int conv = 0;
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-	if (c->use_dedup) {
+	if (c->use_fast) {
+		*c->h_budget = max_shots < 0 ? (1ll << 60) : max_shots;
+		const long long budget0 = *c->h_budget;
+		CUDA_TRY(cudaMemcpyAsync(c->budget.p, c->h_budget, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		while (true) {
+			// a round runs ~rows shots; enqueue a few rounds per host round trip
+			const long long left = budget0 - done;
+			const int rounds = (int)std::max<long long>(1, std::min<long long>(4, (left + c->rows - 1) / c->rows));
+			for (int i = 0; i < rounds; i++)
+				if ((rc = launch_fast_round(c, nullptr))) return rc;
+			if ((rc = read_flags(c))) return rc;
+			done = *c->h_shots - before;
+			if (c->h_flags->converged) { conv = 1; break; }
+			if (*c->h_budget <= 0) break;
+		}
+	} else if (c->use_dedup) {
 		if (!c->have_current) { launch_select(c, c->rec.p + c->cur, 0); c->have_current = true; }
 		while (max_shots < 0 || done < max_shots) {
 			long long batch = kBatchShots;

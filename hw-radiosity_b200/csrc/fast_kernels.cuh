@@ -1,0 +1,354 @@
+// Fast path of the single-source shooting loop (sm_100a).
+//
+// Observation: the form factors of a shot depend only on WHICH patch shoots (pure geometry on a
+// frozen mesh), not on the radiosity state; only the cheap per-receiver update is serial from shot
+// to shot.  And the next shooters are predictable: they are (almost always) the patches with the
+// largest unshot energy now.  So the loop is split into rounds of three kernels:
+//
+//   predict_kernel   top-K candidates by unshot energy (exact top-1 + per-group maxima), form-factor
+//                    cache rows assigned to the ones not cached yet, their shooter records built (K2).
+//   ff_batch_kernel  K3a for all new rows at once: (row, half, unique vertex) items; facing culls first,
+//                    survivors compacted through shared memory so every lane of a warp walks a ray;
+//                    K x 2U rays per launch fill the 148 SMs and hide the walk's dependent-load latency.
+//   shots_kernel     persistent cooperative kernel, one CTA per SM slot: up to `budget` shots, each =
+//                    K3b update from the cached row + block argmax + ONE grid barrier + every CTA
+//                    reducing the per-CTA partials redundantly (K1).  It returns when the next shooter
+//                    has no cached row (misprediction), on convergence, or when the budget is spent.
+//
+// Results are bit-identical to the per-shot kernels of shoot_kernels.cuh: same arithmetic, same
+// selection rule; prediction only decides which form factors are ready, never which patch shoots.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "shoot_kernels.cuh"
+
+namespace radk {
+
+constexpr int kPredictGroups = 2048;	// groups for the approximate top-K (power of two)
+constexpr int kMaxRows = 64;		// upper bound of form-factor cache rows
+
+struct ShotRec {		// the shooter of the next shot, handed from shot to shot / kernel to kernel
+	int slot;		// TriStore slot, -1 none
+	int row;		// cache row holding its form factors, -1 = not cached
+	float dB[3];		// its unshot energy at selection time (what CalRadiosity multiplies by)
+	int valid;
+	int pad[2];
+};
+
+struct Partial {		// one CTA's best candidate of a shot
+	unsigned long long key;
+	float dB[3];
+	int pad;
+};
+
+struct FastState {
+	float2 *ff;			// [rows][U] cached form factors: .x toward half 0, .y toward half 1
+	int rows;			// cache capacity (<= kMaxRows)
+	int *row_slot;			// [rows] slot whose form factors the row holds, -1 free
+	int *slot_row;			// [trinum] row of a slot, -1 none
+	ShooterRec *rec;		// [rows] shooter record per row
+	int *todo;			// [rows] rows to fill in the next ff_batch launch
+	int *ntodo;
+	unsigned long long *group_key;	// [kPredictGroups]
+	unsigned *ticket;
+	ShotRec *handoff;		// current shooter between kernels
+	Partial *partial;		// [2][max CTAs]
+	unsigned *barrier;		// grid barrier counter (zeroed before each shots launch)
+	long long *budget;		// shots the current radk_ctx_step call may still run
+	int *stalled;			// 1: shots_kernel stopped on a cache miss
+};
+
+// ---- predict ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
+	__shared__ unsigned long long keys[kPredictGroups];
+	__shared__ bool s_last;
+	__shared__ int s_ntodo;
+	const int T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	// thread t only sees receivers r == t (mod T); T is a multiple of kPredictGroups, so its running
+	// maximum belongs to group t % kPredictGroups
+	unsigned long long best = 0ull;
+	for (int r = gtid; r < S.R; r += T) {
+		unsigned c;
+		const unsigned long long k = candidate_key(S, S.st[0][r].w, S.st[1][r].w, S.st[2][r].w, __ldg(&S.slot[r]), ~0ull, &c);
+		best = k > best ? k : best;
+	}
+	if (best) atomicMax(&F.group_key[gtid & (kPredictGroups - 1)], best);
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = (atomicAdd(F.ticket, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	// ---- last CTA: sort the group maxima (descending), rebuild the cache around the top `rows`
+	for (int i = threadIdx.x; i < kPredictGroups; i += blockDim.x) {
+		keys[i] = __ldcg(&F.group_key[i]);
+		F.group_key[i] = 0ull;			// ready for the next round
+	}
+	__syncthreads();
+	for (int k = 2; k <= kPredictGroups; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int i = threadIdx.x; i < kPredictGroups; i += blockDim.x) {
+				const int ixj = i ^ j;
+				if (ixj > i) {
+					const unsigned long long a = keys[i], b = keys[ixj];
+					const bool desc = (i & k) == 0;
+					if (desc ? a < b : a > b) keys[i] = b, keys[ixj] = a;
+				}
+			}
+			__syncthreads();
+		}
+	if (threadIdx.x == 0) {
+		*F.ticket = 0u;
+		const int rows = F.rows;
+		// keep only rows whose slot is still among the top candidates
+		int keep[kMaxRows];
+		for (int j = 0; j < rows; j++) keep[j] = 0;
+		int ncand = 0;
+		for (; ncand < rows && keys[ncand] != 0ull; ncand++) {
+			const int row = F.slot_row[(int)(keys[ncand] & 0xffffffffu)];
+			if (row >= 0) keep[row] = 1;
+		}
+		for (int j = 0; j < rows; j++)
+			if (!keep[j] && F.row_slot[j] >= 0) F.slot_row[F.row_slot[j]] = -1, F.row_slot[j] = -1;
+		int nt = 0, free_row = 0;
+		for (int i = 0; i < ncand; i++) {
+			const int slot = (int)(keys[i] & 0xffffffffu);
+			if (F.slot_row[slot] >= 0) continue;
+			while (free_row < rows && F.row_slot[free_row] >= 0) free_row++;
+			if (free_row >= rows) break;
+			F.row_slot[free_row] = slot, F.slot_row[slot] = free_row, F.todo[nt++] = free_row;
+		}
+		*F.ntodo = nt;
+		s_ntodo = nt;
+		// the exact argmax (keys[0]) is the next shooter
+		ShotRec h;
+		h.pad[0] = h.pad[1] = 0;
+		if (keys[0] == 0ull) {
+			h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
+			*S.sel.converged = 1;
+		} else {
+			h.slot = (int)(keys[0] & 0xffffffffu);
+			h.row = F.slot_row[h.slot];
+			const int r = S.slot_to_recv[h.slot];
+			h.dB[0] = S.st[0][r].w, h.dB[1] = S.st[1][r].w, h.dB[2] = S.st[2][r].w;
+			h.valid = 1;
+		}
+		*F.handoff = h;
+		*F.stalled = 0;
+	}
+	__syncthreads();
+	if (threadIdx.x < s_ntodo) {	// K2 for the new rows, one thread each
+		const int row = F.todo[threadIdx.x];
+		build_shooter(S, S.slot_to_recv[F.row_slot[row]], &F.rec[row]);
+	}
+}
+
+// ---- batched form factors -----------------------------------------------------------------------
+constexpr int kFFBlock = 256;
+constexpr int kFFItems = 2;	// candidate vertices per thread before compaction
+
+__global__ void __launch_bounds__(kFFBlock) ff_batch_kernel(DevScene S, FastState F) {
+	const int j = blockIdx.z;
+	if (j >= *F.ntodo) return;
+	const int row = F.todo[j], half = blockIdx.y;
+	__shared__ ShooterRec sh;
+	__shared__ int q_u[kFFBlock * kFFItems];
+	__shared__ float q_ff[kFFBlock * kFFItems];
+	__shared__ int wcount[kFFItems * (kFFBlock / 32)];
+	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)(F.rec + row))[threadIdx.x];
+	__syncthreads();
+	float2 *out = F.ff + (size_t)row * S.U;
+	const int base = blockIdx.x * (kFFBlock * kFFItems);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (!sh.splittable && half == 1) {	// the single centre sample is handled by half 0
+		for (int it = 0; it < kFFItems; it++) {
+			const int u = base + it * kFFBlock + threadIdx.x;
+			if (u < S.U) out[u].y = 0.0f;
+		}
+		return;
+	}
+	const FFSample smp = sh.splittable ? sh.half[half] : sh.centre;
+	// phase 1: culls + analytic form factor; survivors are queued in vertex order
+	float ffv[kFFItems];
+	bool live[kFFItems];
+	unsigned ball[kFFItems];
+#pragma unroll
+	for (int it = 0; it < kFFItems; it++) {
+		const int u = base + it * kFFBlock + threadIdx.x;
+		live[it] = false, ffv[it] = 0.0f;
+		if (u < S.U) {
+			const float4 v = __ldg(&S.uv[u]);
+			const float4 pn = __ldg(&S.par_n[__float_as_int(v.w)]);
+			float dx, dy, dz;
+			ffv[it] = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live[it]);
+			if (!live[it]) { if (half) out[u].y = 0.0f; else out[u].x = 0.0f; }
+		}
+		ball[it] = __ballot_sync(0xffffffffu, live[it]);
+		if (lane == 0) wcount[it * (kFFBlock / 32) + warp] = __popc(ball[it]);
+	}
+	__syncthreads();
+	int total = 0;
+#pragma unroll
+	for (int it = 0; it < kFFItems; it++) {
+		int off = 0;
+		for (int w = 0; w < kFFItems * (kFFBlock / 32); w++) {
+			const int c = wcount[w];
+			if (w < it * (kFFBlock / 32) + warp) off += c;
+			if (it == 0) total += c;
+		}
+		if (live[it]) {
+			const int pos = off + __popc(ball[it] & ((1u << lane) - 1u));
+			q_u[pos] = base + it * kFFBlock + threadIdx.x;
+			q_ff[pos] = ffv[it];
+		}
+	}
+	__syncthreads();
+	// phase 2: every lane walks one surviving ray
+	for (int i = threadIdx.x; i < total; i += kFFBlock) {
+		const int u = q_u[i];
+		const float4 v = __ldg(&S.uv[u]);
+		const float dx = smp.cx - v.x, dy = smp.cy - v.y, dz = smp.cz - v.z;
+		const int hit = ray_walk<false>(S.tree, v.x, v.y, v.z, dx, dy, dz, __float_as_int(v.w), nullptr);
+		const float ff = (hit == sh.logsrc) ? q_ff[i] : 0.0f;
+		if (half) out[u].y = ff; else out[u].x = ff;
+	}
+}
+
+// ---- persistent shot loop -----------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(counter, 1u);
+		while (*((volatile unsigned *)counter) < target) { }
+		__threadfence();
+	}
+	__syncthreads();
+}
+
+constexpr int kShotsBlock = 512;
+
+__global__ void __launch_bounds__(kShotsBlock) shots_kernel(DevScene S, FastState F, int max_ctas) {
+	__shared__ ShotRec cur;
+	__shared__ unsigned long long s_key[kShotsBlock / 32];
+	__shared__ float s_dB[kShotsBlock / 32][3];
+	__shared__ Partial s_best;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int nctas = gridDim.x;
+	// contiguous chunk of receivers per CTA: its state lines stay in this SM's L1 from shot to shot
+	const int per = (S.R + nctas - 1) / nctas;
+	const int r_begin = blockIdx.x * per, r_end = min(S.R, r_begin + per);
+	if (threadIdx.x == 0) {
+		cur = *F.handoff;
+		if (cur.valid) cur.row = F.slot_row[cur.slot];
+	}
+	__syncthreads();
+	long long budget = *F.budget;
+	unsigned epoch = 0;
+	int parity = 0;
+	long long done = 0;
+	int stalled = 0;
+	while (true) {
+		if (!cur.valid || budget <= 0) break;
+		if (cur.row < 0) { stalled = 1; break; }
+		const float2 *ffrow = F.ff + (size_t)cur.row * S.U;
+		const int shooter_slot = cur.slot;
+		const float sdB0 = cur.dB[0], sdB1 = cur.dB[1], sdB2 = cur.dB[2];
+		unsigned long long key = 0ull;
+		float kd0 = 0.f, kd1 = 0.f, kd2 = 0.f;
+		for (int r = r_begin + threadIdx.x; r < r_end; r += kShotsBlock) {
+			float4 a0 = S.st[0][r], a1 = S.st[1][r], a2 = S.st[2][r];
+			const int slot = __ldg(&S.slot[r]);
+			if (slot == shooter_slot) {
+				a0.w = a1.w = a2.w = 0.0f;	// rad.cpp:446-449
+				S.st[0][r].w = 0.0f, S.st[1][r].w = 0.0f, S.st[2][r].w = 0.0f;
+			} else if (a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
+				   a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f) {
+				const int4 id = __ldg(&S.vid[r]);
+				const float2 h0 = __ldcg(&ffrow[id.x]), h1 = __ldcg(&ffrow[id.y]), h2 = __ldcg(&ffrow[id.z]);
+				const float ff[3] = {h0.x + h0.y, h1.x + h1.y, h2.x + h2.y};
+				const float4 fk = __ldg(&S.par_fk[id.w]);
+				const float lo[3] = {fk.x * sdB0 / 3, fk.y * sdB1 / 3, fk.z * sdB2 / 3};	// shade.cpp:247-249
+				float dB[3] = {a0.w, a1.w, a2.w};
+				float4 *acc[3] = {&a0, &a1, &a2};
+#pragma unroll
+				for (int v = 0; v < 3; v++) {
+					float d;
+					d = lo[0] * ff[v]; dB[0] += d; acc[v]->x += d;
+					d = lo[1] * ff[v]; dB[1] += d; acc[v]->y += d;
+					d = lo[2] * ff[v]; dB[2] += d; acc[v]->z += d;
+				}
+				a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
+				S.st[0][r] = a0, S.st[1][r] = a1, S.st[2][r] = a2;
+			}
+			unsigned c;
+			const unsigned long long k = candidate_key(S, a0.w, a1.w, a2.w, slot, ~0ull, &c);
+			if (k > key) key = k, kd0 = a0.w, kd1 = a1.w, kd2 = a2.w;
+		}
+		// CTA argmax carrying the winner's unshot energy
+		const unsigned long long wmax = warp_max_u64(key);
+		const unsigned src = __ffs(__ballot_sync(0xffffffffu, key == wmax && wmax != 0ull)) - 1;
+		if (wmax != 0ull) {
+			kd0 = __shfl_sync(0xffffffffu, kd0, src), kd1 = __shfl_sync(0xffffffffu, kd1, src), kd2 = __shfl_sync(0xffffffffu, kd2, src);
+		}
+		if (lane == 0) s_key[warp] = wmax, s_dB[warp][0] = kd0, s_dB[warp][1] = kd1, s_dB[warp][2] = kd2;
+		__syncthreads();
+		if (warp == 0) {
+			unsigned long long k = lane < kShotsBlock / 32 ? s_key[lane] : 0ull;
+			const unsigned long long m = warp_max_u64(k);
+			const unsigned w = __ffs(__ballot_sync(0xffffffffu, k == m)) - 1;	// some lane < 16 holds m (possibly 0)
+			if (lane == 0) {
+				Partial p;
+				p.key = m, p.dB[0] = s_dB[w][0], p.dB[1] = s_dB[w][1], p.dB[2] = s_dB[w][2], p.pad = 0;
+				F.partial[parity * max_ctas + blockIdx.x] = p;
+			}
+		}
+		epoch++;
+		grid_barrier(F.barrier, epoch * (unsigned)nctas);
+		// every CTA reduces all partials the same way -> identical `cur` everywhere, no second barrier
+		{
+			unsigned long long k = 0ull;
+			int who = -1;
+			for (int b = threadIdx.x; b < nctas; b += kShotsBlock) {
+				const unsigned long long kb = __ldcg(&F.partial[parity * max_ctas + b].key);
+				if (kb > k) k = kb, who = b;
+			}
+			const unsigned long long m1 = warp_max_u64(k);
+			if (lane == 0) s_key[warp] = m1;
+			__syncthreads();
+			unsigned long long m = 0ull;
+			for (int w = 0; w < kShotsBlock / 32; w++) m = s_key[w] > m ? s_key[w] : m;
+			if (m != 0ull && k == m) {	// exactly one thread of the CTA holds the winner
+				const Partial *p = &F.partial[parity * max_ctas + who];
+				s_best.key = m, s_best.dB[0] = __ldcg(&p->dB[0]), s_best.dB[1] = __ldcg(&p->dB[1]), s_best.dB[2] = __ldcg(&p->dB[2]);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				if (blockIdx.x == 0) S.sel.shot_log[(*S.sel.shots_done + done) % S.sel.shot_log_cap] = shooter_slot;
+				ShotRec n;
+				n.pad[0] = n.pad[1] = 0;
+				if (m == 0ull) {
+					n.slot = -1, n.row = -1, n.dB[0] = n.dB[1] = n.dB[2] = 0.0f, n.valid = 0;
+				} else {
+					n.slot = (int)(m & 0xffffffffu);
+					n.row = F.slot_row[n.slot];
+					n.dB[0] = s_best.dB[0], n.dB[1] = s_best.dB[1], n.dB[2] = s_best.dB[2];
+					n.valid = 1;
+				}
+				cur = n;
+			}
+			__syncthreads();
+		}
+		done++, budget--, parity ^= 1;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		*F.handoff = cur;
+		*F.budget = budget;
+		*S.sel.shots_done += done;
+		atomicAdd(&S.stats->shots, (unsigned long long)done);
+		*F.stalled = stalled;
+		if (!cur.valid) *S.sel.converged = 1;
+	}
+}
+
+}  // namespace radk

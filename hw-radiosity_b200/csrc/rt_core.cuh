@@ -36,6 +36,7 @@ struct DevTree {
 	float G0[3], G1[3];
 	float min_grid_len;
 	int grid_num;
+	double inv_min_grid_len;	// 1.0 / (double)min_grid_len, see leaf_of
 };
 // occluder record (the {n, c, se} of TriStore[idx] at shot time, raycast.cpp:288-309):
 //   q0 = n.x n.y n.z c.x | q1 = c.y c.z se00 se01 | q2 = se02 se03 se10 se11
@@ -73,14 +74,27 @@ RADK_HD float dot3(float ax, float ay, float az, float bx, float by, float bz) {
 	return ax * bx + ay * by + az * bz;
 }
 
+// gnum = (int)(((double)q - G0) / MinGridLen) (raycast.cpp:263).  The double division is replaced by a
+// multiplication with the rounded reciprocal; both results differ from the exact quotient by less
+// than 1e-13, so their truncations can only disagree when the quotient lies within 1e-9 of an
+// integer - in that case the reference's division is evaluated instead.  Bit-identical by construction.
+RADK_HD int cell_index(const DevTree &T, float q, float g0) {
+	const double x = (double)q - (double)g0;
+	const double y = x * T.inv_min_grid_len;
+	int n = (int)y;
+	const double fr = y - (double)n;
+	if (fr < 1e-9 || fr > 0.999999999) n = (int)(x / (double)T.min_grid_len);
+	return n;
+}
+
 // TreeNodeNum (raycast.cpp:254-281): leaf containing q, or -1 outside the scene cube.
 template <bool STATS>
 RADK_HD int leaf_of(const DevTree &T, float qx, float qy, float qz, WalkCounters *wc) {
 	if (qx < T.G0[0] || qx > T.G1[0] || qy < T.G0[1] || qy > T.G1[1] || qz < T.G0[2] || qz > T.G1[2])
 		return -1;
-	int gx = (int)(((double)qx - (double)T.G0[0]) / (double)T.min_grid_len);
-	int gy = (int)(((double)qy - (double)T.G0[1]) / (double)T.min_grid_len);
-	int gz = (int)(((double)qz - (double)T.G0[2]) / (double)T.min_grid_len);
+	int gx = cell_index(T, qx, T.G0[0]);
+	int gy = cell_index(T, qy, T.G0[1]);
+	int gz = cell_index(T, qz, T.G0[2]);
 	// every index >= grid_num takes the all-upper path of the descent, negatives the all-lower one
 	const int g = T.grid_num, dim = g + 1;
 	gx = gx < 0 ? 0 : (gx > g ? g : gx);
@@ -96,8 +110,10 @@ RADK_HD bool tri_hit(const float4 *o, float px, float py, float pz, float vx, fl
 	const float4 q0 = ldg(o), q1 = ldg(o + 1);
 	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
 	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
+	// t = a2/a1 < 0.0001 is certain when the signs differ (or a2 is zero): skip the division.
+	if ((a1 > 0.0f && a2 <= 0.0f) || (a1 < 0.0f && a2 >= 0.0f)) return false;
 	const float t = a2 / a1;
-	if ((double)t < 0.0001) return false;
+	if (t <= 0.0001f) return false;	// == ((double)t < 0.0001): 0.0001f is the largest float below the double 0.0001
 	if (t >= t_min) return false;
 	const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
 	const float4 q2 = ldg(o + 2);
@@ -149,11 +165,11 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 		}
 		if (hit >= 0) return hit;
 		prev = cur;
-		// NextPoint
+		// NextPoint; fabsf(v) > 1e-6f == (fabs((double)v) > 1e-6): 1e-6f is below the double 1e-6
 		float tn = 1000000.0f, s;
-		if (fabs((double)vx) > 1e-6) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
-		if (fabs((double)vy) > 1e-6) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
-		if (fabs((double)vz) > 1e-6) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
+		if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
+		if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
+		if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
 		tn = (float)((double)tn + 0.1);
 		qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
 		t = tn;
@@ -172,12 +188,13 @@ struct FFSample {
 
 struct FFCounters { unsigned calff, rays, visible; };
 
-// CalFF (shade.cpp:107-127).  desLen = norm(receiver normal) is passed in (pure function of n).
-template <bool STATS>
-RADK_HD float cal_ff(const DevTree &T, const FFSample &S, int logsrc, float ndx, float ndy, float ndz, float desLen,
-		     int logdest, float px, float py, float pz, FFCounters *fc, WalkCounters *wc) {
-	if (STATS) fc->calff++;
-	const float dx = S.cx - px, dy = S.cy - py, dz = S.cz - pz;
+// The part of CalFF before the ray (shade.cpp:109-123): facing culls and the analytic point-to-patch
+// form factor.  Returns 0 when the sample is culled, otherwise the (positive, possibly NaN) form
+// factor that CalFF returns if the ray then reaches the shooter; dir = sample centre - p.
+RADK_HD float ff_geom(const FFSample &S, float ndx, float ndy, float ndz, float desLen, float px, float py, float pz,
+		      float &dx, float &dy, float &dz, bool &cast) {
+	dx = S.cx - px, dy = S.cy - py, dz = S.cz - pz;
+	cast = false;
 	const float dotSrc = dot3(dx, dy, dz, S.nx, S.ny, S.nz);
 	const float dotDes = -dot3(dx, dy, dz, ndx, ndy, ndz);
 	if ((dotSrc < 0) != (dotDes < 0)) return 0.0f;
@@ -189,6 +206,19 @@ RADK_HD float cal_ff(const DevTree &T, const FFSample &S, int logsrc, float ndx,
 	if (ff <= 0.0f) return 0.0f;
 	ff = (float)((double)ff * ((double)S.area / ((double)n2 * 3.1415926535897932)));
 	if (ff <= 0.0f) return 0.0f;
+	cast = true;	// NaN form factors pass both tests and do cast a ray, like the reference
+	return ff;
+}
+
+// CalFF (shade.cpp:107-127).  desLen = norm(receiver normal) is passed in (pure function of n).
+template <bool STATS>
+RADK_HD float cal_ff(const DevTree &T, const FFSample &S, int logsrc, float ndx, float ndy, float ndz, float desLen,
+		     int logdest, float px, float py, float pz, FFCounters *fc, WalkCounters *wc) {
+	if (STATS) fc->calff++;
+	float dx, dy, dz;
+	bool cast;
+	const float ff = ff_geom(S, ndx, ndy, ndz, desLen, px, py, pz, dx, dy, dz, cast);
+	if (!cast) return 0.0f;
 	if (STATS) fc->rays++;
 	if (ray_walk<STATS>(T, px, py, pz, dx, dy, dz, logdest, wc) == logsrc) {
 		if (STATS) fc->visible++;

@@ -38,6 +38,7 @@ struct FlatScene {
 		T.list = list.data(), T.occ = occ.data();
 		for (int k = 0; k < 3; k++) T.G0[k] = s->G0[k], T.G1[k] = s->G1[k];
 		T.min_grid_len = s->min_grid_len, T.grid_num = s->grid_num;
+		T.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
 		return T;
 	}
 };

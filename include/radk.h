@@ -86,7 +86,10 @@ typedef struct radk_opts {
 	int collect_stats;	/* 1: count rays / visits / tests on the device (slower kernels) */
 	int dedup;		/* 1 (default when 0 is not forced by split_enabled): evaluate each unique
 				 * (vertex, parent) once per shot; -1: force per-receiver evaluation */
-	int reserved[6];
+	int per_shot_kernels;	/* 1: run every shot as its own kernel pair (K3a, K3b) instead of the batched
+				 * predict / form-factor-cache / persistent-loop path (same results) */
+	int ff_rows;		/* form-factor cache rows (shooters evaluated per batch); 0 = default 32 */
+	int reserved[4];
 } radk_opts;
 
 typedef struct radk_stats {
@@ -181,10 +184,13 @@ int radk_ctx_snapshot_colors(radk_ctx *c, int *rgb, int trinum);
 int radk_ctx_stats(radk_ctx *c, radk_stats *st);
 /* Device time (ms, CUDA events on the context's stream) spent inside radk_ctx_step so far. */
 double radk_ctx_device_ms(const radk_ctx *c);
-/* Profiling aid: runs up to nshots single-source shots with a CUDA-event pair around every kernel
- * launch and returns the average device time (ms) per launch of K3a (vertex_ff_kernel) and K3b
- * (update_select_kernel), and the number of shots actually run. */
-int radk_ctx_kernel_times(radk_ctx *c, int nshots, double *k3a_ms, double *k3b_ms, int *shots_run);
+/* Profiling aid: runs up to max_shots shots (max_shots < 0: to convergence) with a CUDA-event pair
+ * around every kernel launch on the context's stream and accumulates device time per kernel class:
+ *   ms[0]/n[0] selection   (predict_kernel, or select_kernel on the per-shot path)
+ *   ms[1]/n[1] visibility + form factors (ff_batch_kernel, or vertex_ff_kernel)   <- the traversal
+ *   ms[2]/n[2] radiosity update + argmax (shots_kernel, or update_select_kernel)
+ * n[] = launches per class; *shots = shots run. */
+int radk_ctx_profile(radk_ctx *c, long long max_shots, double ms[3], long long n[3], long long *shots);
 /* Sizes of this context's shard: receivers, unique vertices, occluders, octree nodes. */
 int radk_ctx_sizes(const radk_ctx *c, int *receivers, int *unique_vertices, int *occluders, int *nodes);
 

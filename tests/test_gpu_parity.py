@@ -71,6 +71,44 @@ def test_convergence_matches_golden_and_fin_bytes(hr, golden, models_dir, name):
     assert hashlib.sha256(m.format()).hexdigest() == g["fin_sha"]        # byte-identical .fin
 
 
+@pytest.mark.parametrize("name", ["church", "blocks", "model1", "sbox", "model3s"])
+def test_fast_path_convergence_matches_golden(hr, golden, models_dir, name):
+    """The batched path (predict / form-factor cache / persistent shot loop) must shoot the same
+    patches in the same order and end in the same bits as the reference."""
+    g = golden["models"][name]["full"]
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    ctx = hr.Context(m)                      # collect_stats=0 -> fast path
+    done, conv = ctx.step(-1)
+    assert conv and done == g["shots"]
+    assert ctx.shooter_log() == [s[0] for s in g["shooters"]]
+    ctx.download_into(m)
+    d = state_digest(m.triangles)
+    assert d["accB_sha"] == g["accB_sha"] and d["deltaB_sha"] == g["deltaB_sha"]
+
+
+@pytest.mark.parametrize("name,shots", [("box", 300), ("room", 150), ("hall", 60)])
+def test_fast_path_equals_per_shot_kernels(hr, models_dir, name, shots):
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    a, b = hr.Context(m), hr.Context(m, per_shot_kernels=1)
+    assert a.step(shots)[0] == shots and b.step(shots)[0] == shots
+    assert a.shooter_log() == b.shooter_log()
+    for x, y in zip(a.download(), b.download()):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+def test_small_cache_and_budget_edges(hr, models_dir):
+    m = hr.Model(str(models_dir / "model3s.tri"))
+    ref = hr.Context(m, per_shot_kernels=1)
+    ref.step(101)
+    for rows in (2, 5):
+        c = hr.Context(m, ff_rows=rows)
+        for k in (1, 2, 33, 65):
+            assert c.step(k) == (k, False)
+        assert c.shooter_log() == ref.shooter_log()
+        for x, y in zip(c.download(), ref.download()):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
 def test_stats_off_gives_identical_state(hr, models_dir):
     m = hr.Model(str(models_dir / "sbox.tri"))
     a, b = hr.Context(m, collect_stats=1), hr.Context(m, collect_stats=0)
