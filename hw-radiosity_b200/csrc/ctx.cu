@@ -67,7 +67,9 @@ struct radk_ctx {
 	std::vector<int> recv_slot;		// receiver index -> slot (this shard)
 	std::vector<int> recv_parent;
 
-	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot;
+	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot, leaf_list4, tri_leaf_begin, tri_leaves;
+	DevBuf<int4> list4;
+	DevBuf<unsigned> row_mask;
 	DevBuf<float4> leaf_lo, leaf_hi, occ, geo[3], st[3], st0[3], uv, par_n, par_fk;
 	DevBuf<int4> vid;
 	DevBuf<float2> ffh;
@@ -128,7 +130,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	predict_kernel<<<64, 1024, 0, st>>>(c->S, c->F);
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
-	ff_batch_kernel<<<g, kFFBlock, 0, st>>>(c->S, c->F);
+	ff_batch_kernel<<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	int max_ctas = c->shots_ctas;
 	void *args[] = {(void *)&c->S, (void *)&c->F, (void *)&max_ctas};
@@ -155,6 +157,10 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(c->leaf_lo.upload(F.leaf_lo, st));
 	CUDA_TRY(c->leaf_hi.upload(F.leaf_hi, st));
 	CUDA_TRY(c->list.upload(F.list, st));
+	CUDA_TRY(c->list4.upload(F.list4, st));
+	CUDA_TRY(c->leaf_list4.upload(F.leaf_list4, st));
+	CUDA_TRY(c->tri_leaf_begin.upload(F.tri_leaf_begin, st));
+	CUDA_TRY(c->tri_leaves.upload(F.tri_leaves, st));
 	CUDA_TRY(c->occ.upload(F.occ, st));
 	for (int v = 0; v < 3; v++) {
 		CUDA_TRY(c->geo[v].upload(F.geo[v], st));
@@ -209,11 +215,14 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		CUDA_TRY(c->handoff.alloc(1));
 		CUDA_TRY(c->partial.alloc(2 * (size_t)c->shots_ctas));
 		CUDA_TRY(c->budget.alloc(1));
+		const int mask_words = (s->nnodes + 31) / 32;
+		CUDA_TRY(c->row_mask.alloc((size_t)kMaxRows * mask_words));
 		FastState &F = c->F;
 		F.ff = c->ffcache.p, F.rows = rows, F.row_slot = c->row_slot.p, F.slot_row = c->slot_row.p;
 		F.rec = c->row_rec.p, F.todo = c->todo.p, F.ntodo = c->fast_ints.p, F.stalled = c->fast_ints.p + 1;
 		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.barrier = c->fast_uints.p + 1;
 		F.handoff = c->handoff.p, F.partial = c->partial.p, F.budget = c->budget.p;
+		F.row_mask = c->row_mask.p, F.mask_words = mask_words;
 		int rc2 = reset_fast_state(c);
 		if (rc2) return rc2;
 	}
@@ -230,6 +239,9 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	S.tree.leaf_lo = c->leaf_lo.p;
 	S.tree.leaf_hi = c->leaf_hi.p;
 	S.tree.list = c->list.p;
+	S.tree.list4 = c->list4.p, S.tree.leaf_list4 = c->leaf_list4.p;
+	S.tree.tri_leaf_begin = c->tri_leaf_begin.p, S.tree.tri_leaves = c->tri_leaves.p;
+	S.tree.nnodes = s->nnodes;
 	S.tree.occ = c->occ.p;
 	for (int k = 0; k < 3; k++) S.tree.G0[k] = s->G0[k], S.tree.G1[k] = s->G1[k];
 	S.tree.min_grid_len = s->min_grid_len;

@@ -24,8 +24,8 @@
 
 namespace radk {
 
-constexpr int kPredictGroups = 2048;	// groups for the approximate top-K (power of two)
-constexpr int kMaxRows = 64;		// upper bound of form-factor cache rows
+constexpr int kPredictGroups = 2048;	// groups for the approximate top-K (= 2 keys per thread of the last CTA)
+constexpr int kMaxRows = 32;		// upper bound of form-factor cache rows (one ballot word)
 
 struct ShotRec {		// the shooter of the next shot, handed from shot to shot / kernel to kernel
 	int slot;		// TriStore slot, -1 none
@@ -55,12 +55,13 @@ struct FastState {
 	Partial *partial;		// [2][max CTAs]
 	unsigned *barrier;		// grid barrier counter (zeroed before each shots launch)
 	long long *budget;		// shots the current radk_ctx_step call may still run
+	unsigned *row_mask;		// [rows][mask_words] bit n set <=> leaf n's list contains the row's logsrc
+	int mask_words;
 	int *stalled;			// 1: shots_kernel stopped on a cache miss
 };
 
 // ---- predict ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
-	__shared__ unsigned long long keys[kPredictGroups];
 	__shared__ bool s_last;
 	__shared__ int s_ntodo;
 	const int T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,75 +80,103 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence();
-	// ---- last CTA: sort the group maxima (descending), rebuild the cache around the top `rows`
-	for (int i = threadIdx.x; i < kPredictGroups; i += blockDim.x) {
-		keys[i] = __ldcg(&F.group_key[i]);
-		F.group_key[i] = 0ull;			// ready for the next round
+	// ---- last CTA: the `rows` largest group maxima, by repeated CTA-wide argmax (each thread owns two keys)
+	__shared__ unsigned long long wmax[2][32];
+	__shared__ unsigned long long top[kMaxRows];
+	unsigned long long k0 = __ldcg(&F.group_key[threadIdx.x]), k1 = __ldcg(&F.group_key[threadIdx.x + 1024]);
+	F.group_key[threadIdx.x] = 0ull, F.group_key[threadIdx.x + 1024] = 0ull;	// ready for the next round
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int rows = F.rows;
+	for (int it = 0; it < rows; it++) {
+		const unsigned long long mine = k0 > k1 ? k0 : k1;
+		const unsigned long long wm = warp_max_u64(mine);
+		if (lane == 0) wmax[it & 1][warp] = wm;
+		__syncthreads();
+		const unsigned long long m = warp_max_u64(wmax[it & 1][lane]);	// every warp reduces the 32 warp maxima
+		if (m != 0ull) {
+			if (k0 == m) k0 = 0ull;
+			if (k1 == m) k1 = 0ull;
+		}
+		if (threadIdx.x == 0) top[it] = m;
 	}
 	__syncthreads();
-	for (int k = 2; k <= kPredictGroups; k <<= 1)
-		for (int j = k >> 1; j > 0; j >>= 1) {
-			for (int i = threadIdx.x; i < kPredictGroups; i += blockDim.x) {
-				const int ixj = i ^ j;
-				if (ixj > i) {
-					const unsigned long long a = keys[i], b = keys[ixj];
-					const bool desc = (i & k) == 0;
-					if (desc ? a < b : a > b) keys[i] = b, keys[ixj] = a;
-				}
+	// ---- warp 0 rebuilds the cache around the candidates: lane j owns candidate j and row j
+	if (warp == 0) {
+		if (lane == 0) *F.ticket = 0u;
+		const unsigned long long key = lane < rows ? top[lane] : 0ull;
+		const bool valid = key != 0ull;
+		const int slot = (int)(key & 0xffffffffu);
+		int row = valid ? F.slot_row[slot] : -1;
+		// rows still wanted
+		unsigned keepmask = 0u;
+		for (int j = 0; j < 32; j++) {
+			const int rj = __shfl_sync(0xffffffffu, row, j);
+			if (rj >= 0) keepmask |= 1u << rj;
+		}
+		int held = lane < rows ? F.row_slot[lane] : 0;		// slot held by row `lane`
+		if (lane < rows && held >= 0 && !((keepmask >> lane) & 1u)) {
+			F.slot_row[held] = -1, F.row_slot[lane] = -1, held = -1;
+		}
+		const unsigned freemask = __ballot_sync(0xffffffffu, lane < rows && held < 0);
+		const bool need = valid && row < 0;
+		const unsigned needmask = __ballot_sync(0xffffffffu, need);
+		const int rank = __popc(needmask & ((1u << lane) - 1u));
+		const int nfree = __popc(freemask), nneed = __popc(needmask);
+		if (need && rank < nfree) {
+			row = (int)__fns(freemask, 0, rank + 1);
+			F.row_slot[row] = slot, F.slot_row[slot] = row, F.todo[rank] = row;
+		}
+		const int nt = nneed < nfree ? nneed : nfree;
+		if (lane == 0) {
+			*F.ntodo = nt;
+			s_ntodo = nt;
+			// the exact argmax (top[0]) is the next shooter
+			ShotRec h;
+			h.pad[0] = h.pad[1] = 0;
+			if (!valid) {
+				h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
+				*S.sel.converged = 1;
+			} else {
+				h.slot = slot;
+				h.row = row;
+				const int r = S.slot_to_recv[slot];
+				h.dB[0] = S.st[0][r].w, h.dB[1] = S.st[1][r].w, h.dB[2] = S.st[2][r].w;
+				h.valid = 1;
 			}
-			__syncthreads();
+			*F.handoff = h;
+			*F.stalled = 0;
 		}
-	if (threadIdx.x == 0) {
-		*F.ticket = 0u;
-		const int rows = F.rows;
-		// keep only rows whose slot is still among the top candidates
-		int keep[kMaxRows];
-		for (int j = 0; j < rows; j++) keep[j] = 0;
-		int ncand = 0;
-		for (; ncand < rows && keys[ncand] != 0ull; ncand++) {
-			const int row = F.slot_row[(int)(keys[ncand] & 0xffffffffu)];
-			if (row >= 0) keep[row] = 1;
-		}
-		for (int j = 0; j < rows; j++)
-			if (!keep[j] && F.row_slot[j] >= 0) F.slot_row[F.row_slot[j]] = -1, F.row_slot[j] = -1;
-		int nt = 0, free_row = 0;
-		for (int i = 0; i < ncand; i++) {
-			const int slot = (int)(keys[i] & 0xffffffffu);
-			if (F.slot_row[slot] >= 0) continue;
-			while (free_row < rows && F.row_slot[free_row] >= 0) free_row++;
-			if (free_row >= rows) break;
-			F.row_slot[free_row] = slot, F.slot_row[slot] = free_row, F.todo[nt++] = free_row;
-		}
-		*F.ntodo = nt;
-		s_ntodo = nt;
-		// the exact argmax (keys[0]) is the next shooter
-		ShotRec h;
-		h.pad[0] = h.pad[1] = 0;
-		if (keys[0] == 0ull) {
-			h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
-			*S.sel.converged = 1;
-		} else {
-			h.slot = (int)(keys[0] & 0xffffffffu);
-			h.row = F.slot_row[h.slot];
-			const int r = S.slot_to_recv[h.slot];
-			h.dB[0] = S.st[0][r].w, h.dB[1] = S.st[1][r].w, h.dB[2] = S.st[2][r].w;
-			h.valid = 1;
-		}
-		*F.handoff = h;
-		*F.stalled = 0;
 	}
 	__syncthreads();
-	if (threadIdx.x < s_ntodo) {	// K2 for the new rows, one thread each
+	const int nt = s_ntodo;
+	if (threadIdx.x < nt) {	// K2 for the new rows, one thread each
 		const int row = F.todo[threadIdx.x];
 		build_shooter(S, S.slot_to_recv[F.row_slot[row]], &F.rec[row]);
+	}
+	// leaf masks of the new rows: which leaves list the shooter's original triangle
+	for (int t = 0; t < nt; t++) {
+		unsigned *mask = F.row_mask + (size_t)F.todo[t] * F.mask_words;
+		for (int w = threadIdx.x; w < F.mask_words; w += blockDim.x) mask[w] = 0u;
+	}
+	__syncthreads();
+	for (int t = 0; t < nt; t++) {
+		const int row = F.todo[t];
+		const int logsrc = __float_as_int(S.geo[0][S.slot_to_recv[F.row_slot[row]]].w);
+		unsigned *mask = F.row_mask + (size_t)row * F.mask_words;
+		const int b = S.tree.tri_leaf_begin[logsrc], e = S.tree.tri_leaf_begin[logsrc + 1];
+		for (int k = b + threadIdx.x; k < e; k += blockDim.x) {
+			const int leaf = S.tree.tri_leaves[k];
+			atomicOr(&mask[leaf >> 5], 1u << (leaf & 31));
+		}
 	}
 }
 
 // ---- batched form factors -----------------------------------------------------------------------
 constexpr int kFFBlock = 256;
-constexpr int kFFItems = 2;	// candidate vertices per thread before compaction
+constexpr int kFFItems = 4;	// candidate vertices per thread before compaction
 
 __global__ void __launch_bounds__(kFFBlock) ff_batch_kernel(DevScene S, FastState F) {
+	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;
 	const int row = F.todo[j], half = blockIdx.y;
@@ -155,7 +184,10 @@ __global__ void __launch_bounds__(kFFBlock) ff_batch_kernel(DevScene S, FastStat
 	__shared__ int q_u[kFFBlock * kFFItems];
 	__shared__ float q_ff[kFFBlock * kFFItems];
 	__shared__ int wcount[kFFItems * (kFFBlock / 32)];
+	__shared__ int s_next;
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)(F.rec + row))[threadIdx.x];
+	for (int w = threadIdx.x; w < F.mask_words; w += kFFBlock) s_mask[w] = F.row_mask[(size_t)row * F.mask_words + w];
+	if (threadIdx.x == 0) s_next = 0;
 	__syncthreads();
 	float2 *out = F.ff + (size_t)row * S.U;
 	const int base = blockIdx.x * (kFFBlock * kFFItems);
@@ -168,6 +200,7 @@ __global__ void __launch_bounds__(kFFBlock) ff_batch_kernel(DevScene S, FastStat
 		return;
 	}
 	const FFSample smp = sh.splittable ? sh.half[half] : sh.centre;
+	const int logsrc = sh.logsrc;
 	// phase 1: culls + analytic form factor; survivors are queued in vertex order
 	float ffv[kFFItems];
 	bool live[kFFItems];
@@ -203,14 +236,71 @@ __global__ void __launch_bounds__(kFFBlock) ff_batch_kernel(DevScene S, FastStat
 		}
 	}
 	__syncthreads();
-	// phase 2: every lane walks one surviving ray
-	for (int i = threadIdx.x; i < total; i += kFFBlock) {
-		const int u = q_u[i];
-		const float4 v = __ldg(&S.uv[u]);
-		const float dx = smp.cx - v.x, dy = smp.cy - v.y, dz = smp.cz - v.z;
-		const int hit = ray_walk<false>(S.tree, v.x, v.y, v.z, dx, dy, dz, __float_as_int(v.w), nullptr);
-		const float ff = (hit == sh.logsrc) ? q_ff[i] : 0.0f;
-		if (half) out[u].y = ff; else out[u].x = ff;
+	// phase 2: every lane walks rays from the queue; a lane whose ray is decided fetches the next one
+	// at the following leaf step, so lanes stay busy although rays visit different numbers of leaves.
+	const DevTree &T = S.tree;
+	int i = -1, u = 0, ban = 0, prev = -1, guard = 0;
+	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, qx = 0, qy = 0, qz = 0, t = 0, ffq = 0;
+	for (;;) {
+		if (i < 0) {
+			i = atomicAdd(&s_next, 1);
+			if (i >= total) break;
+			u = q_u[i], ffq = q_ff[i];
+			const float4 v = __ldg(&S.uv[u]);
+			px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
+			vx = smp.cx - px, vy = smp.cy - py, vz = smp.cz - pz;
+			qx = px, qy = py, qz = pz, prev = -1, guard = 0, t = 0.f;
+		}
+		int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
+		const int cur = leaf_of<false>(T, qx, qy, qz, nullptr);
+		if (cur < 0) {
+			verdict = 0;
+		} else if (prev == cur) {		// raycast.cpp:344-351
+			t = (float)((double)t + 1.0);
+			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
+			if (++guard > 100000) verdict = 0;
+		} else {
+			const float4 lo = __ldg(&T.leaf_lo[cur]);
+			const float4 hi = __ldg(&T.leaf_hi[cur]);
+			if ((s_mask[cur >> 5] >> (cur & 31)) & 1u) {
+				int hit = -1;
+				float t_min = 1000000.0f;
+				const int *lp = T.list + __float_as_int(lo.w);
+				int idx;
+				while ((idx = __ldg(lp++)) >= 0) {
+					if (idx == ban) continue;
+					if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
+				}
+				if (hit >= 0) verdict = (hit == logsrc);
+			} else {
+				const int4 *l4 = T.list4 + __ldg(&T.leaf_list4[cur]);
+				for (;;) {
+					const int4 id = __ldg(l4++);
+					bool any = false;
+					if (id.x >= 0 && id.x != ban) any |= tri_accept_first(T.occ + (size_t)id.x * OCC_STRIDE, px, py, pz, vx, vy, vz);
+					if (id.y >= 0 && id.y != ban) any |= tri_accept_first(T.occ + (size_t)id.y * OCC_STRIDE, px, py, pz, vx, vy, vz);
+					if (id.z >= 0 && id.z != ban) any |= tri_accept_first(T.occ + (size_t)id.z * OCC_STRIDE, px, py, pz, vx, vy, vz);
+					if (id.w >= 0 && id.w != ban) any |= tri_accept_first(T.occ + (size_t)id.w * OCC_STRIDE, px, py, pz, vx, vy, vz);
+					if (any) { verdict = 0; break; }
+					if (id.w < 0) break;
+				}
+			}
+			if (verdict < 0) {	// NextPoint (raycast.cpp:235-251)
+				prev = cur;
+				float tn = 1000000.0f, s;
+				if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
+				if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
+				if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
+				tn = (float)((double)tn + 0.1);
+				qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
+				t = tn;
+			}
+		}
+		if (verdict >= 0) {
+			const float ff = verdict ? ffq : 0.0f;
+			if (half) out[u].y = ff; else out[u].x = ff;
+			i = -1;
+		}
 	}
 }
 

@@ -32,6 +32,11 @@ struct DevTree {
 	const float4 *leaf_lo;		// per node: g0.xyz | list offset (int bits)
 	const float4 *leaf_hi;		// per node: g1.xyz | depth (int bits, statistics only)
 	const int *list;		// leaf lists, -1 terminated, ascending triangle index
+	const int4 *list4;		// the same lists, each padded with -1 to a multiple of 4 entries (16 B aligned)
+	const int *leaf_list4;		// per node: offset (in int4 units) of its padded list, -1 for inner nodes
+	const int *tri_leaf_begin;	// [n0+1] inverted index: leaves whose list contains triangle i ...
+	const int *tri_leaves;		// ... are tri_leaves[tri_leaf_begin[i] .. tri_leaf_begin[i+1])
+	int nnodes;
 	const float4 *occ;		// 5 float4 per occluder, see OCC_* below
 	float G0[3], G1[3];
 	float min_grid_len;
@@ -175,6 +180,70 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 		t = tn;
 	}
 	return -1;
+}
+
+// Is the shooter visible?  Same answer as (ray_walk(...) == logsrc), organised for the GPU:
+//  * `has_src` is a bitmask over octree nodes: bit set <=> the leaf's list contains logsrc.  In a leaf
+//    WITHOUT logsrc any accepted triangle ends the walk with "not visible" - which triangle is nearest
+//    does not matter, and whether *some* triangle is accepted does not depend on the scan order
+//    (the first acceptance always happens against t_min = 1e6).  Those leaves are scanned four list
+//    entries at a time with independent tests (no loop-carried t_min), stopping at the first accept.
+//  * a leaf WITH logsrc runs the reference's sequential nearest-hit scan unchanged.
+RADK_HD bool tri_accept_first(const float4 *o, float px, float py, float pz, float vx, float vy, float vz) {
+	float t_min = 1000000.0f;
+	return tri_hit(o, px, py, pz, vx, vy, vz, t_min);
+}
+
+template <typename MaskPtr>
+RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, float pz, float vx, float vy, float vz,
+		      int ban, int logsrc) {
+	float t = 0.f;
+	int prev = -1, cur;
+	float qx = px, qy = py, qz = pz;
+	int guard = 0;
+	while ((cur = leaf_of<false>(T, qx, qy, qz, nullptr)) >= 0) {
+		if (prev == cur) {		// raycast.cpp:344-351
+			t = (float)((double)t + 1.0);
+			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
+			if (++guard > 100000) return false;
+			continue;
+		}
+		const float4 lo = ldg(&T.leaf_lo[cur]);
+		const float4 hi = ldg(&T.leaf_hi[cur]);
+		if ((has_src[cur >> 5] >> (cur & 31)) & 1u) {
+			// exact nearest-hit scan (TriListHitted, raycast.cpp:316-333)
+			int hit = -1;
+			float t_min = 1000000.0f;
+			const int *lp = T.list + float_as_int_hd(lo.w);
+			int idx;
+			while ((idx = ldg(lp++)) >= 0) {
+				if (idx == ban) continue;
+				if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
+			}
+			if (hit >= 0) return hit == logsrc;
+		} else {
+			const int4 *l4 = T.list4 + ldg(&T.leaf_list4[cur]);
+			for (;;) {
+				const int4 id = ldg(l4++);
+				bool any = false;
+				if (id.x >= 0 && id.x != ban) any |= tri_accept_first(T.occ + (size_t)id.x * OCC_STRIDE, px, py, pz, vx, vy, vz);
+				if (id.y >= 0 && id.y != ban) any |= tri_accept_first(T.occ + (size_t)id.y * OCC_STRIDE, px, py, pz, vx, vy, vz);
+				if (id.z >= 0 && id.z != ban) any |= tri_accept_first(T.occ + (size_t)id.z * OCC_STRIDE, px, py, pz, vx, vy, vz);
+				if (id.w >= 0 && id.w != ban) any |= tri_accept_first(T.occ + (size_t)id.w * OCC_STRIDE, px, py, pz, vx, vy, vz);
+				if (any) return false;		// some other triangle is hit in this leaf: the walk ends, shooter not returned
+				if (id.w < 0) break;		// padding reached: end of list
+			}
+		}
+		prev = cur;
+		float tn = 1000000.0f, s;
+		if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
+		if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
+		if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
+		tn = (float)((double)tn + 0.1);
+		qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
+		t = tn;
+	}
+	return false;
 }
 
 // ---- form factor ---------------------------------------------------------------------------------

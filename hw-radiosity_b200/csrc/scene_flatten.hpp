@@ -21,6 +21,8 @@ struct FlatScene {
 	std::vector<int> cell_leaf;
 	std::vector<float4> leaf_lo, leaf_hi;
 	std::vector<int> list;
+	std::vector<int4> list4;
+	std::vector<int> leaf_list4, tri_leaf_begin, tri_leaves;
 	std::vector<float4> occ;
 	// receivers of this shard
 	int R = 0, U = 0, leaves_total = 0;
@@ -36,6 +38,9 @@ struct FlatScene {
 		DevTree T;
 		T.cell_leaf = cell_leaf.data(), T.leaf_lo = leaf_lo.data(), T.leaf_hi = leaf_hi.data();
 		T.list = list.data(), T.occ = occ.data();
+		T.list4 = list4.data(), T.leaf_list4 = leaf_list4.data();
+		T.tri_leaf_begin = tri_leaf_begin.data(), T.tri_leaves = tri_leaves.data();
+		T.nnodes = (int)leaf_lo.size();
 		for (int k = 0; k < 3; k++) T.G0[k] = s->G0[k], T.G1[k] = s->G1[k];
 		T.min_grid_len = s->min_grid_len, T.grid_num = s->grid_num;
 		T.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
@@ -104,6 +109,38 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 		F.leaf_hi[i] = f4(nd.g1[0], nd.g1[1], nd.g1[2], ibits(depth[i]));
 	}
 	F.list.assign(s->list, s->list + s->nlist);
+	// padded copies of the leaf lists + inverted index triangle -> leaves
+	F.leaf_list4.assign(s->nnodes, -1);
+	F.list4.clear();
+	std::vector<std::vector<int>> leaves_of(s->n0);
+	for (int i = 0; i < s->nnodes; i++) {
+		const int off = s->nodes[i].list;
+		if (off < 0) continue;
+		if (off >= s->nlist) { F.error = "leaf list offset out of range"; return RADK_ERR_ARG; }
+		F.leaf_list4[i] = (int)F.list4.size();
+		int buf[4], nb = 0;
+		for (int k = off;; k++) {
+			if (k >= s->nlist) { F.error = "unterminated leaf list"; return RADK_ERR_ARG; }
+			const int idx = s->list[k];
+			if (idx >= s->n0) { F.error = "leaf list references a non-input triangle"; return RADK_ERR_ARG; }
+			buf[nb++] = idx < 0 ? -1 : idx;
+			if (idx >= 0 && (leaves_of[idx].empty() || leaves_of[idx].back() != i)) leaves_of[idx].push_back(i);
+			if (nb == 4 || idx < 0) {
+				while (nb < 4) buf[nb++] = -1;
+				F.list4.push_back(i4(buf[0], buf[1], buf[2], buf[3]));
+				nb = 0;
+				if (idx < 0) break;
+			}
+		}
+		if (F.list4.back().w >= 0) F.list4.push_back(i4(-1, -1, -1, -1));	// a full last chunk still needs a terminator
+	}
+	F.tri_leaf_begin.assign(s->n0 + 1, 0);
+	F.tri_leaves.clear();
+	for (int i = 0; i < s->n0; i++) {
+		F.tri_leaf_begin[i] = (int)F.tri_leaves.size();
+		F.tri_leaves.insert(F.tri_leaves.end(), leaves_of[i].begin(), leaves_of[i].end());
+	}
+	F.tri_leaf_begin[s->n0] = (int)F.tri_leaves.size();
 	F.occ.resize((size_t)s->n0 * OCC_STRIDE);
 	for (int i = 0; i < s->n0; i++) {
 		const radk_triangle &t = s->tri[i];

@@ -37,6 +37,9 @@ int emu_rays(const radk_scene *s, const float *p, const float *v, const int *fro
 // Runs `shots` single-source shots the way the kernels do (unique-vertex form factors, then the
 // per-receiver update with the fused argmax) and writes accB[trinum][3][3], deltaB[trinum][3] and
 // the shooter slot of every shot.  counters[0..2] = reference-equivalent rays, visible, shaded receivers.
+static int g_mode = 0;	// 0: cal_ff / ray_walk (per-shot kernels); 1: ff_geom + ray_sees (batched fast path)
+void emu_set_mode(int mode) { g_mode = mode; }
+
 int emu_run(const radk_scene *s, float converge, int rank, int world, int shots, float *accB, float *deltaB,
 	    int *shooters, int *nshots_out, long long *counters) {
 	FlatScene F;
@@ -66,7 +69,38 @@ int emu_run(const radk_scene *s, float converge, int rank, int world, int shots,
 	int done = 0;
 	ShooterRec sh;
 	select(&sh);
+	std::vector<unsigned> mask((T.nnodes + 31) / 32);
 	while (done < shots && sh.valid) {
+		if (g_mode == 1) {	// ff_batch_kernel: per-row leaf mask, culls first, then the any-hit walk
+			std::fill(mask.begin(), mask.end(), 0u);
+			for (int k = T.tri_leaf_begin[sh.logsrc]; k < T.tri_leaf_begin[sh.logsrc + 1]; k++)
+				mask[T.tri_leaves[k] >> 5] |= 1u << (T.tri_leaves[k] & 31);
+			for (int u = 0; u < U; u++) {
+				const float4 v = F.uv[u];
+				const int parent = float_as_int_hd(v.w);
+				const float4 pn = F.par_n[parent];
+				unsigned nr = 0, nv = 0;
+				float out[2] = {0.0f, 0.0f};
+				const int nh = sh.splittable ? 2 : 1;
+				for (int h = 0; h < nh; h++) {
+					const FFSample &smp = sh.splittable ? sh.half[h] : sh.centre;
+					float dx, dy, dz;
+					bool cast;
+					const float ff = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, cast);
+					if (!cast) continue;
+					nr++;
+					if (ray_sees(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc)) out[h] = ff, nv++;
+				}
+				if (sh.splittable) {	// the discarded centre sample, for reference-equivalent counts only
+					float dx, dy, dz;
+					bool cast;
+					ff_geom(sh.centre, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, cast);
+					if (cast) nr++, nv += ray_sees(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc);
+				}
+				ff0[u] = out[0], ff1[u] = out[1];
+				vstat[u] = nr | (nv << 8);
+			}
+		} else
 		for (int u = 0; u < U; u++) {	// vertex_ff_kernel
 			const float4 v = F.uv[u];
 			const int parent = float_as_int_hd(v.w);
