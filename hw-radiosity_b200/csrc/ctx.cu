@@ -91,7 +91,8 @@ struct radk_ctx {
 	DevBuf<long long> budget;
 	FastState F{};
 	bool use_fast = false;
-	int rows = 0, shots_ctas = 0;
+	int rows = 0, shots_ctas = 0, shots_rpt = 0;
+	const void *shots_fn = nullptr;
 	long long *h_budget = nullptr;		// pinned
 	int max_blocks = 0;
 	int cur = 0;				// which of rec[0]/rec[1] holds the current shooter
@@ -134,7 +135,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	int max_ctas = c->shots_ctas;
 	void *args[] = {(void *)&c->S, (void *)&c->F, (void *)&max_ctas};
-	CUDA_TRY(cudaLaunchCooperativeKernel((const void *)shots_kernel, dim3((unsigned)c->shots_ctas), dim3(kShotsBlock), args, 0, st));
+	CUDA_TRY(cudaLaunchCooperativeKernel(c->shots_fn, dim3((unsigned)c->shots_ctas), dim3(kShotsBlock), args, 0, st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
 	c->launches += 3;
 	return RADK_OK;
@@ -198,12 +199,26 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		int rows = o.ff_rows > 0 ? std::min(o.ff_rows, kMaxRows) : 32;
 		while (rows > 2 && (size_t)rows * std::max(U, 1) * sizeof(float2) > free_b / 4) rows >>= 1;
 		c->rows = rows;
-		int dev_sms = 0, per_sm = 0;
+		int dev_sms = 0;
 		CUDA_TRY(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device));
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shots_kernel, kShotsBlock, 0));
-		per_sm = std::max(1, std::min(per_sm, 2));
-		// no more CTAs than there is work for (a CTA needs a few receivers per thread to be worth a barrier slot)
-		c->shots_ctas = std::max(1, std::min(dev_sms * per_sm, (R + kShotsBlock - 1) / kShotsBlock));
+		// shot-loop variant: receivers resident in registers when the shard fits (1, 2 or 4 per thread), else streamed
+		struct { int rpt; const void *fn; } variants[] = {{1, (const void *)shots_kernel<1>}, {2, (const void *)shots_kernel<2>},
+								 {4, (const void *)shots_kernel<4>}, {0, (const void *)shots_kernel<0>}};
+		c->shots_rpt = -1;
+		for (auto &v : variants) {
+			int per_sm = 0;
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, kShotsBlock, 0));
+			if (per_sm < 1) continue;
+			per_sm = std::min(per_sm, 2);
+			const int max_ctas = dev_sms * per_sm;
+			const int cap = max_ctas * kShotsBlock * std::max(v.rpt, 1);
+			if (v.rpt > 0 && R > cap) continue;
+			c->shots_rpt = v.rpt, c->shots_fn = v.fn;
+			// no more CTAs than there is work for
+			c->shots_ctas = std::max(1, std::min(max_ctas, (R + kShotsBlock * std::max(v.rpt, 1) - 1) / (kShotsBlock * std::max(v.rpt, 1))));
+			break;
+		}
+		if (c->shots_rpt < 0) { set_error("shots_kernel does not fit this device"); return RADK_ERR_CUDA; }
 		CUDA_TRY(c->ffcache.alloc((size_t)rows * std::max(U, 1)));
 		CUDA_TRY(c->row_slot.alloc(kMaxRows));
 		CUDA_TRY(c->slot_row.alloc(std::max(s->trinum, 1)));

@@ -318,19 +318,63 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
 
 constexpr int kShotsBlock = 512;
 
-__global__ void __launch_bounds__(kShotsBlock) shots_kernel(DevScene S, FastState F, int max_ctas) {
+// CalRadiosity (shade.cpp:244-259) of one receiver from cached vertex form factors.
+__device__ __forceinline__ void apply_shot(float4 &a0, float4 &a1, float4 &a2, const int4 &id, const float4 &fk,
+					   const float2 *__restrict__ ffrow, float sdB0, float sdB1, float sdB2) {
+	const float2 h0 = __ldcg(&ffrow[id.x]), h1 = __ldcg(&ffrow[id.y]), h2 = __ldcg(&ffrow[id.z]);
+	const float ff[3] = {h0.x + h0.y, h1.x + h1.y, h2.x + h2.y};
+	const float lo[3] = {fk.x * sdB0 / 3, fk.y * sdB1 / 3, fk.z * sdB2 / 3};	// shade.cpp:247-249
+	float dB[3] = {a0.w, a1.w, a2.w};
+	float4 *acc[3] = {&a0, &a1, &a2};
+#pragma unroll
+	for (int v = 0; v < 3; v++) {
+		float d;
+		d = lo[0] * ff[v]; dB[0] += d; acc[v]->x += d;
+		d = lo[1] * ff[v]; dB[1] += d; acc[v]->y += d;
+		d = lo[2] * ff[v]; dB[2] += d; acc[v]->z += d;
+	}
+	a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
+}
+__device__ __forceinline__ bool unsaturated(const float4 &a0, const float4 &a1, const float4 &a2) {	// rad.cpp:424-428
+	return a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
+	       a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f;
+}
+
+// RPT > 0: every thread keeps the state, vertex ids and reflectance of RPT receivers in registers for
+// the whole launch (the shard fits gridDim * 512 * RPT); RPT == 0: receivers are streamed from L2/HBM
+// every shot (any shard size).
+template <int RPT>
+__global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(DevScene S, FastState F, int max_ctas) {
 	__shared__ ShotRec cur;
 	__shared__ unsigned long long s_key[kShotsBlock / 32];
 	__shared__ float s_dB[kShotsBlock / 32][3];
 	__shared__ Partial s_best;
+	constexpr int NR = RPT > 0 ? RPT : 1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nctas = gridDim.x;
-	// contiguous chunk of receivers per CTA: its state lines stay in this SM's L1 from shot to shot
+	// contiguous chunk of receivers per CTA
 	const int per = (S.R + nctas - 1) / nctas;
 	const int r_begin = blockIdx.x * per, r_end = min(S.R, r_begin + per);
 	if (threadIdx.x == 0) {
 		cur = *F.handoff;
 		if (cur.valid) cur.row = F.slot_row[cur.slot];
+	}
+	// resident receivers
+	float4 ra0[NR], ra1[NR], ra2[NR], rfk[NR];
+	int4 rid[NR];
+	int rslot[NR];
+	if (RPT > 0) {
+#pragma unroll
+		for (int k = 0; k < NR; k++) {
+			const int r = r_begin + threadIdx.x + k * kShotsBlock;
+			rslot[k] = -1;
+			if (r < r_end) {
+				ra0[k] = S.st[0][r], ra1[k] = S.st[1][r], ra2[k] = S.st[2][r];
+				rid[k] = __ldg(&S.vid[r]);
+				rfk[k] = __ldg(&S.par_fk[rid[k].w]);
+				rslot[k] = __ldg(&S.slot[r]);
+			}
+		}
 	}
 	__syncthreads();
 	long long budget = *F.budget;
@@ -346,34 +390,32 @@ __global__ void __launch_bounds__(kShotsBlock) shots_kernel(DevScene S, FastStat
 		const float sdB0 = cur.dB[0], sdB1 = cur.dB[1], sdB2 = cur.dB[2];
 		unsigned long long key = 0ull;
 		float kd0 = 0.f, kd1 = 0.f, kd2 = 0.f;
-		for (int r = r_begin + threadIdx.x; r < r_end; r += kShotsBlock) {
-			float4 a0 = S.st[0][r], a1 = S.st[1][r], a2 = S.st[2][r];
-			const int slot = __ldg(&S.slot[r]);
-			if (slot == shooter_slot) {
-				a0.w = a1.w = a2.w = 0.0f;	// rad.cpp:446-449
-				S.st[0][r].w = 0.0f, S.st[1][r].w = 0.0f, S.st[2][r].w = 0.0f;
-			} else if (a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
-				   a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f) {
-				const int4 id = __ldg(&S.vid[r]);
-				const float2 h0 = __ldcg(&ffrow[id.x]), h1 = __ldcg(&ffrow[id.y]), h2 = __ldcg(&ffrow[id.z]);
-				const float ff[3] = {h0.x + h0.y, h1.x + h1.y, h2.x + h2.y};
-				const float4 fk = __ldg(&S.par_fk[id.w]);
-				const float lo[3] = {fk.x * sdB0 / 3, fk.y * sdB1 / 3, fk.z * sdB2 / 3};	// shade.cpp:247-249
-				float dB[3] = {a0.w, a1.w, a2.w};
-				float4 *acc[3] = {&a0, &a1, &a2};
+		if (RPT > 0) {
 #pragma unroll
-				for (int v = 0; v < 3; v++) {
-					float d;
-					d = lo[0] * ff[v]; dB[0] += d; acc[v]->x += d;
-					d = lo[1] * ff[v]; dB[1] += d; acc[v]->y += d;
-					d = lo[2] * ff[v]; dB[2] += d; acc[v]->z += d;
-				}
-				a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
-				S.st[0][r] = a0, S.st[1][r] = a1, S.st[2][r] = a2;
+			for (int k = 0; k < NR; k++) {
+				if (rslot[k] < 0) continue;
+				if (rslot[k] == shooter_slot) ra0[k].w = ra1[k].w = ra2[k].w = 0.0f;	// rad.cpp:446-449
+				else if (unsaturated(ra0[k], ra1[k], ra2[k])) apply_shot(ra0[k], ra1[k], ra2[k], rid[k], rfk[k], ffrow, sdB0, sdB1, sdB2);
+				unsigned c;
+				const unsigned long long kk = candidate_key(S, ra0[k].w, ra1[k].w, ra2[k].w, rslot[k], ~0ull, &c);
+				if (kk > key) key = kk, kd0 = ra0[k].w, kd1 = ra1[k].w, kd2 = ra2[k].w;
 			}
-			unsigned c;
-			const unsigned long long k = candidate_key(S, a0.w, a1.w, a2.w, slot, ~0ull, &c);
-			if (k > key) key = k, kd0 = a0.w, kd1 = a1.w, kd2 = a2.w;
+		} else {
+			for (int r = r_begin + threadIdx.x; r < r_end; r += kShotsBlock) {
+				float4 a0 = S.st[0][r], a1 = S.st[1][r], a2 = S.st[2][r];
+				const int slot = __ldg(&S.slot[r]);
+				if (slot == shooter_slot) {
+					a0.w = a1.w = a2.w = 0.0f;
+					S.st[0][r].w = 0.0f, S.st[1][r].w = 0.0f, S.st[2][r].w = 0.0f;
+				} else if (unsaturated(a0, a1, a2)) {
+					const int4 id = __ldg(&S.vid[r]);
+					apply_shot(a0, a1, a2, id, __ldg(&S.par_fk[id.w]), ffrow, sdB0, sdB1, sdB2);
+					S.st[0][r] = a0, S.st[1][r] = a1, S.st[2][r] = a2;
+				}
+				unsigned c;
+				const unsigned long long kk = candidate_key(S, a0.w, a1.w, a2.w, slot, ~0ull, &c);
+				if (kk > key) key = kk, kd0 = a0.w, kd1 = a1.w, kd2 = a2.w;
+			}
 		}
 		// CTA argmax carrying the winner's unshot energy
 		const unsigned long long wmax = warp_max_u64(key);
@@ -430,6 +472,13 @@ __global__ void __launch_bounds__(kShotsBlock) shots_kernel(DevScene S, FastStat
 			__syncthreads();
 		}
 		done++, budget--, parity ^= 1;
+	}
+	if (RPT > 0) {	// write the resident state back
+#pragma unroll
+		for (int k = 0; k < NR; k++) {
+			const int r = r_begin + threadIdx.x + k * kShotsBlock;
+			if (rslot[k] >= 0) S.st[0][r] = ra0[k], S.st[1][r] = ra1[k], S.st[2][r] = ra2[k];
+		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		*F.handoff = cur;
