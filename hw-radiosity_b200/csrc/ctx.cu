@@ -428,21 +428,26 @@ int radk_ctx_profile(radk_ctx *c, long long max_shots, double ms[3], long long n
 	if (rc) return rc;
 	const long long before = *c->h_shots;
 	for (int k = 0; k < 3; k++) ms[k] = 0, n[k] = 0;
-	cudaEvent_t ev[4];
+	constexpr int kProfRounds = 8;
+	cudaEvent_t ev[4 * kProfRounds];
 	for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
 	const bool stats = c->opt.collect_stats != 0;
 	long long done = 0;
 	if (c->use_fast) {
 		*c->h_budget = max_shots < 0 ? (1ll << 60) : max_shots;
 		CUDA_TRY(cudaMemcpyAsync(c->budget.p, c->h_budget, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
 		while (true) {
-			if ((rc = launch_fast_round(c, ev))) return rc;
+			// several rounds are enqueued back to back so the GPU never waits for the host between kernels
+			for (int i = 0; i < kProfRounds; i++)
+				if ((rc = launch_fast_round(c, ev + 4 * i))) return rc;
 			if ((rc = read_flags(c))) return rc;
-			for (int k = 0; k < 3; k++) {
-				float t = 0;
-				CUDA_TRY(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
-				ms[k] += t, n[k]++;
-			}
+			for (int i = 0; i < kProfRounds; i++)
+				for (int k = 0; k < 3; k++) {
+					float t = 0;
+					CUDA_TRY(cudaEventElapsedTime(&t, ev[4 * i + k], ev[4 * i + k + 1]));
+					ms[k] += t, n[k]++;
+				}
 			done = *c->h_shots - before;
 			if (c->h_flags->converged || *c->h_budget <= 0) break;
 		}

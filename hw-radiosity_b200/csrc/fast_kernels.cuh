@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 constexpr int kFFBlock = 256;
 constexpr int kFFItems = 4;	// candidate vertices per thread before compaction
 
-__global__ void __launch_bounds__(kFFBlock) ff_batch_kernel(DevScene S, FastState F) {
+__global__ void __launch_bounds__(kFFBlock, 3) ff_batch_kernel(DevScene S, FastState F) {
 	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;
@@ -273,17 +273,7 @@ __global__ void __launch_bounds__(kFFBlock) ff_batch_kernel(DevScene S, FastStat
 				}
 				if (hit >= 0) verdict = (hit == logsrc);
 			} else {
-				const int4 *l4 = T.list4 + __ldg(&T.leaf_list4[cur]);
-				for (;;) {
-					const int4 id = __ldg(l4++);
-					bool any = false;
-					if (id.x >= 0 && id.x != ban) any |= tri_accept_first(T.occ + (size_t)id.x * OCC_STRIDE, px, py, pz, vx, vy, vz);
-					if (id.y >= 0 && id.y != ban) any |= tri_accept_first(T.occ + (size_t)id.y * OCC_STRIDE, px, py, pz, vx, vy, vz);
-					if (id.z >= 0 && id.z != ban) any |= tri_accept_first(T.occ + (size_t)id.z * OCC_STRIDE, px, py, pz, vx, vy, vz);
-					if (id.w >= 0 && id.w != ban) any |= tri_accept_first(T.occ + (size_t)id.w * OCC_STRIDE, px, py, pz, vx, vy, vz);
-					if (any) { verdict = 0; break; }
-					if (id.w < 0) break;
-				}
+				if (leaf_any_hit(T, __ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban)) verdict = 0;
 			}
 			if (verdict < 0) {	// NextPoint (raycast.cpp:235-251)
 				prev = cur;

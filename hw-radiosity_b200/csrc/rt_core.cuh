@@ -189,9 +189,60 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 //    (the first acceptance always happens against t_min = 1e6).  Those leaves are scanned four list
 //    entries at a time with independent tests (no loop-carried t_min), stopping at the first accept.
 //  * a leaf WITH logsrc runs the reference's sequential nearest-hit scan unchanged.
-RADK_HD bool tri_accept_first(const float4 *o, float px, float py, float pz, float vx, float vy, float vz) {
-	float t_min = 1000000.0f;
-	return tri_hit(o, px, py, pz, vx, vy, vz, t_min);
+// list4 entries carry a flag for occluders whose three side planes are all zero (the re-split
+// originals of PrePartitionTriangles, SURVEY.md Fact 4): their inside test always passes, so the
+// plane part of TriHitted decides alone and the side-plane loads are skipped.
+constexpr int kPlaneFlag = 1 << 30;
+constexpr int kIdMask = kPlaneFlag - 1;
+
+// Any-hit scan of one leaf list (padded int4 chunks): true iff TriListHitted (raycast.cpp:316-333) would
+// return some triangle.  Two phases per chunk so that the lanes of a warp stay together: (A) the plane
+// part of all four entries - loads, two dot products, the division, the two t tests - without branches;
+// (B) the three side-plane tests only for entries that survived (A), one at a time.
+RADK_HD bool leaf_any_hit(const DevTree &T, int list4_off, float px, float py, float pz, float vx, float vy, float vz, int ban) {
+	const int4 *l4 = T.list4 + list4_off;
+	for (;;) {
+		const int4 id = ldg(l4++);
+		const int ids[4] = {id.x, id.y, id.z, id.w};
+		float tt[4];
+		unsigned cand = 0u;
+		bool plane_hit = false;
+#pragma unroll
+		for (int e = 0; e < 4; e++) {
+			const int idx = ids[e] & kIdMask;
+			const bool valid = ids[e] >= 0 && idx != ban;
+			tt[e] = 0.0f;
+			if (valid) {
+				const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
+				const float4 q0 = ldg(o), q1 = ldg(o + 1);
+				const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
+				const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
+				const float t = a2 / a1;
+				// TriHitted's two rejections with t_min = 1e6; NaN passes both, as in the reference
+				const bool pass = !(t <= 0.0001f) && !(t >= 1000000.0f);
+				tt[e] = t;
+				if (pass) {
+					if (ids[e] & kPlaneFlag) plane_hit = true;
+					else cand |= 1u << e;
+				}
+			}
+		}
+		if (plane_hit) return true;
+		while (cand) {
+			const int e = (cand & 1u) ? 0 : (cand & 2u) ? 1 : (cand & 4u) ? 2 : 3;
+			cand &= cand - 1u;
+			const int idx = (e == 0 ? ids[0] : e == 1 ? ids[1] : e == 2 ? ids[2] : ids[3]) & kIdMask;
+			const float t = e == 0 ? tt[0] : e == 1 ? tt[1] : e == 2 ? tt[2] : tt[3];
+			const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
+			const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
+			const float4 q1 = ldg(o + 1), q2 = ldg(o + 2), q3 = ldg(o + 3), q4 = ldg(o + 4);
+			if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) continue;
+			if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) continue;
+			if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) continue;
+			return true;
+		}
+		if (id.w < 0) return false;	// padding reached: end of list
+	}
 }
 
 template <typename MaskPtr>
@@ -222,17 +273,8 @@ RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, flo
 			}
 			if (hit >= 0) return hit == logsrc;
 		} else {
-			const int4 *l4 = T.list4 + ldg(&T.leaf_list4[cur]);
-			for (;;) {
-				const int4 id = ldg(l4++);
-				bool any = false;
-				if (id.x >= 0 && id.x != ban) any |= tri_accept_first(T.occ + (size_t)id.x * OCC_STRIDE, px, py, pz, vx, vy, vz);
-				if (id.y >= 0 && id.y != ban) any |= tri_accept_first(T.occ + (size_t)id.y * OCC_STRIDE, px, py, pz, vx, vy, vz);
-				if (id.z >= 0 && id.z != ban) any |= tri_accept_first(T.occ + (size_t)id.z * OCC_STRIDE, px, py, pz, vx, vy, vz);
-				if (id.w >= 0 && id.w != ban) any |= tri_accept_first(T.occ + (size_t)id.w * OCC_STRIDE, px, py, pz, vx, vy, vz);
-				if (any) return false;		// some other triangle is hit in this leaf: the walk ends, shooter not returned
-				if (id.w < 0) break;		// padding reached: end of list
-			}
+			// some other triangle is hit in this leaf: the walk ends, shooter not returned
+			if (leaf_any_hit(T, ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban)) return false;
 		}
 		prev = cur;
 		float tn = 1000000.0f, s;

@@ -118,21 +118,23 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 		if (off < 0) continue;
 		if (off >= s->nlist) { F.error = "leaf list offset out of range"; return RADK_ERR_ARG; }
 		F.leaf_list4[i] = (int)F.list4.size();
-		int buf[4], nb = 0;
+		// any-hit order: occluders whose side planes are all zero first (cheapest test, most likely to hit)
+		std::vector<int> planes, others;
 		for (int k = off;; k++) {
 			if (k >= s->nlist) { F.error = "unterminated leaf list"; return RADK_ERR_ARG; }
 			const int idx = s->list[k];
-			if (idx >= s->n0) { F.error = "leaf list references a non-input triangle"; return RADK_ERR_ARG; }
-			buf[nb++] = idx < 0 ? -1 : idx;
-			if (idx >= 0 && (leaves_of[idx].empty() || leaves_of[idx].back() != i)) leaves_of[idx].push_back(i);
-			if (nb == 4 || idx < 0) {
-				while (nb < 4) buf[nb++] = -1;
-				F.list4.push_back(i4(buf[0], buf[1], buf[2], buf[3]));
-				nb = 0;
-				if (idx < 0) break;
-			}
+			if (idx < 0) break;
+			if (idx >= s->n0 || idx >= kPlaneFlag) { F.error = "leaf list references a non-input triangle"; return RADK_ERR_ARG; }
+			if (leaves_of[idx].empty() || leaves_of[idx].back() != i) leaves_of[idx].push_back(i);
+			bool zero_se = true;
+			for (int a = 0; a < 3; a++)
+				for (int b = 0; b < 4; b++) zero_se = zero_se && s->tri[idx].se[a][b] == 0.0f;
+			(zero_se ? planes : others).push_back(zero_se ? (idx | kPlaneFlag) : idx);
 		}
-		if (F.list4.back().w >= 0) F.list4.push_back(i4(-1, -1, -1, -1));	// a full last chunk still needs a terminator
+		planes.insert(planes.end(), others.begin(), others.end());
+		planes.push_back(-1);
+		while (planes.size() % 4) planes.push_back(-1);
+		for (size_t k = 0; k < planes.size(); k += 4) F.list4.push_back(i4(planes[k], planes[k + 1], planes[k + 2], planes[k + 3]));
 	}
 	F.tri_leaf_begin.assign(s->n0 + 1, 0);
 	F.tri_leaves.clear();
