@@ -195,53 +195,44 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 constexpr int kPlaneFlag = 1 << 30;
 constexpr int kIdMask = kPlaneFlag - 1;
 
-// Any-hit scan of one leaf list (padded int4 chunks): true iff TriListHitted (raycast.cpp:316-333) would
-// return some triangle.  Two phases per chunk so that the lanes of a warp stay together: (A) the plane
-// part of all four entries - loads, two dot products, the division, the two t tests - without branches;
-// (B) the three side-plane tests only for entries that survived (A), one at a time.
+// Any-hit scan of one leaf list (int4 chunks of indices, zero-side-plane occluders first): true iff
+// TriListHitted (raycast.cpp:316-333) would return some triangle.  Entries are tested one after the
+// other and the scan stops at the first acceptance (against t_min = 1e6, which is what the reference's
+// first acceptance sees); indices come four per load.
+RADK_HD bool any_hit_one(const DevTree &T, int entry, float px, float py, float pz, float vx, float vy, float vz, int ban) {
+	const int idx = entry & kIdMask;
+	if (idx == ban) return false;
+	const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
+	const float4 q0 = ldg(o), q1 = ldg(o + 1);
+	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
+	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
+	if ((a1 > 0.0f && a2 <= 0.0f) || (a1 < 0.0f && a2 >= 0.0f)) return false;	// t <= 0: certain rejection
+	const float t = a2 / a1;
+	if (t <= 0.0001f) return false;
+	if (t >= 1000000.0f) return false;
+	if (entry & kPlaneFlag) return true;		// all side planes zero: the inside test cannot fail
+	const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
+	const float4 q2 = ldg(o + 2);
+	if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) return false;
+	const float4 q3 = ldg(o + 3);
+	if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) return false;
+	const float4 q4 = ldg(o + 4);
+	if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) return false;
+	return true;
+}
+
 RADK_HD bool leaf_any_hit(const DevTree &T, int list4_off, float px, float py, float pz, float vx, float vy, float vz, int ban) {
 	const int4 *l4 = T.list4 + list4_off;
 	for (;;) {
 		const int4 id = ldg(l4++);
-		const int ids[4] = {id.x, id.y, id.z, id.w};
-		float tt[4];
-		unsigned cand = 0u;
-		bool plane_hit = false;
-#pragma unroll
-		for (int e = 0; e < 4; e++) {
-			const int idx = ids[e] & kIdMask;
-			const bool valid = ids[e] >= 0 && idx != ban;
-			tt[e] = 0.0f;
-			if (valid) {
-				const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
-				const float4 q0 = ldg(o), q1 = ldg(o + 1);
-				const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
-				const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
-				const float t = a2 / a1;
-				// TriHitted's two rejections with t_min = 1e6; NaN passes both, as in the reference
-				const bool pass = !(t <= 0.0001f) && !(t >= 1000000.0f);
-				tt[e] = t;
-				if (pass) {
-					if (ids[e] & kPlaneFlag) plane_hit = true;
-					else cand |= 1u << e;
-				}
-			}
-		}
-		if (plane_hit) return true;
-		while (cand) {
-			const int e = (cand & 1u) ? 0 : (cand & 2u) ? 1 : (cand & 4u) ? 2 : 3;
-			cand &= cand - 1u;
-			const int idx = (e == 0 ? ids[0] : e == 1 ? ids[1] : e == 2 ? ids[2] : ids[3]) & kIdMask;
-			const float t = e == 0 ? tt[0] : e == 1 ? tt[1] : e == 2 ? tt[2] : tt[3];
-			const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
-			const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
-			const float4 q1 = ldg(o + 1), q2 = ldg(o + 2), q3 = ldg(o + 3), q4 = ldg(o + 4);
-			if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) continue;
-			if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) continue;
-			if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) continue;
-			return true;
-		}
-		if (id.w < 0) return false;	// padding reached: end of list
+		if (id.x < 0) return false;
+		if (any_hit_one(T, id.x, px, py, pz, vx, vy, vz, ban)) return true;
+		if (id.y < 0) return false;
+		if (any_hit_one(T, id.y, px, py, pz, vx, vy, vz, ban)) return true;
+		if (id.z < 0) return false;
+		if (any_hit_one(T, id.z, px, py, pz, vx, vy, vz, ban)) return true;
+		if (id.w < 0) return false;
+		if (any_hit_one(T, id.w, px, py, pz, vx, vy, vz, ban)) return true;
 	}
 }
 
