@@ -65,9 +65,8 @@ EXPORTS = [
     "radk_model_write", "radk_model_format", "radk_ctx_create", "radk_ctx_destroy", "radk_ctx_reset",
     "radk_ctx_rewind", "radk_ctx_step", "radk_ctx_select", "radk_ctx_shoot", "radk_ctx_shooter_log", "radk_ctx_trinum",
     "radk_ctx_download", "radk_ctx_download_triangles", "radk_ctx_snapshot_colors", "radk_ctx_stats",
-    "radk_ctx_device_ms", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_vertex_ff", "radk_ctx_local_candidate",
-    "radk_ctx_shoot_candidate", "radk_ctx_candidate_buffer", "radk_ctx_local_candidate_dev",
-    "radk_ctx_shoot_gathered_dev", "radk_ctx_converged_flag",
+    "radk_ctx_device_ms", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_vertex_ff",
+    "radk_ctx_peer_handle", "radk_ctx_peer_connect", "radk_ctx_peer_connect_local", "radk_ctx_owned_slots",
 ]
 
 _lib = None
@@ -130,6 +129,10 @@ def load_library():
     L.radk_ctx_device_ms.argtypes = [vp]
     L.radk_ctx_device_ms.restype = C.c_double
     L.radk_ray_hitted.argtypes = [vp, vp, vp, vp, C.c_int, vp]
+    L.radk_ctx_peer_handle.argtypes = [vp, vp]
+    L.radk_ctx_peer_connect.argtypes = [vp, vp, C.c_int]
+    L.radk_ctx_peer_connect_local.argtypes = [vp, C.POINTER(vp), C.c_int]
+    L.radk_ctx_owned_slots.argtypes = [vp, vp, C.c_int, ip]
     L.radk_vertex_ff.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
     _lib = L
     return L
@@ -318,6 +321,41 @@ class Context:
     @property
     def device_ms(self):
         return load_library().radk_ctx_device_ms(self._h)
+
+    # ---- multi-GPU introductions -----------------------------------------------------------
+    def peer_handle(self):
+        buf = C.create_string_buffer(64)
+        _check(load_library().radk_ctx_peer_handle(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles):
+        blob = b"".join(handles)
+        _check(load_library().radk_ctx_peer_connect(self._h, blob, len(handles)))
+
+    @staticmethod
+    def connect_local(contexts):
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        for c in contexts:
+            _check(load_library().radk_ctx_peer_connect_local(c._h, arr, len(contexts)))
+
+    def owned_slots(self):
+        n = C.c_int()
+        L = load_library()
+        _check(L.radk_ctx_owned_slots(self._h, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.int32)
+        _check(L.radk_ctx_owned_slots(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def shoot(self, slots):
+        arr = (C.c_int * len(slots))(*[int(x) for x in slots])
+        _check(load_library().radk_ctx_shoot(self._h, arr, len(slots)))
+
+    def vertex_ff(self, shooter, receivers, vertices):
+        r = np.ascontiguousarray(receivers, dtype=np.int32)
+        v = np.ascontiguousarray(vertices, dtype=np.int32)
+        out = np.empty(len(r), dtype=np.float32)
+        _check(load_library().radk_vertex_ff(self._h, int(shooter), r.ctypes.data, v.ctypes.data, len(r), out.ctypes.data))
+        return out
 
     def ray_hitted(self, p, v, frm):
         p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)

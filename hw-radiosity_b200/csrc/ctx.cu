@@ -66,6 +66,7 @@ struct radk_ctx {
 	int R = 0, U = 0, leaves_total = 0;
 	std::vector<int> recv_slot;		// receiver index -> slot (this shard)
 	std::vector<int> recv_parent;
+	std::vector<int> h_slot_to_recv;	// slot -> receiver index on this shard, -1 otherwise
 
 	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot, leaf_list4, tri_leaf_begin, tri_leaves;
 	DevBuf<int4> list4;
@@ -79,7 +80,6 @@ struct radk_ctx {
 	DevBuf<long long> shots_done;
 	DevBuf<DevStats> stats;
 	DevBuf<ShooterRec> rec;			// [0],[1]: ping-pong for the single-source loop; [2..]: multi-source list
-	DevBuf<radk_candidate> cand;		// multi-GPU exchange buffer [world]
 	// fast path (fast_kernels.cuh)
 	DevBuf<float2> ffcache;
 	DevBuf<int> row_slot, slot_row, todo, fast_ints;	// fast_ints: [0]=ntodo [1]=stalled
@@ -89,6 +89,13 @@ struct radk_ctx {
 	DevBuf<ShotRec> handoff;
 	DevBuf<Partial> partial;
 	DevBuf<long long> budget;
+	DevBuf<PeerBox> box;
+	DevBuf<unsigned long long> pred_round;
+	DevBuf<int> fast_error;
+	std::vector<void *> ipc_opened;
+	bool peers_connected = false;
+	unsigned long long epoch = 0;
+	int *h_error = nullptr;			// pinned
 	FastState F{};
 	bool use_fast = false;
 	int rows = 0, shots_ctas = 0, shots_rpt = 0;
@@ -119,6 +126,9 @@ int reset_fast_state(radk_ctx *c) {
 	CUDA_TRY(cudaMemsetAsync(c->fast_uints.p, 0, 4 * sizeof(unsigned), st));
 	CUDA_TRY(cudaMemsetAsync(c->handoff.p, 0, sizeof(ShotRec), st));
 	CUDA_TRY(cudaMemsetAsync(c->budget.p, 0, sizeof(long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->pred_round.p, 0, sizeof(unsigned long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->fast_error.p, 0, sizeof(int), st));
+	c->F.epoch = ++c->epoch;	// stale mailbox sequence numbers of earlier runs can never match
 	return RADK_OK;
 }
 
@@ -129,6 +139,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	CUDA_TRY(cudaMemsetAsync(c->F.barrier, 0, sizeof(unsigned), st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
 	predict_kernel<<<64, 1024, 0, st>>>(c->S, c->F);
+	if (c->F.world > 1) { predict_merge_kernel<<<1, 256, 0, st>>>(c->S, c->F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
 	ff_batch_kernel<<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
@@ -154,6 +165,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	c->R = R, c->U = U, c->leaves_total = F.leaves_total;
 	c->recv_slot = F.recv_slot;
 	c->recv_parent = F.recv_parent;
+	c->h_slot_to_recv = F.slot_to_recv;
 	CUDA_TRY(c->cell_leaf.upload(F.cell_leaf, st));
 	CUDA_TRY(c->leaf_lo.upload(F.leaf_lo, st));
 	CUDA_TRY(c->leaf_hi.upload(F.leaf_hi, st));
@@ -190,8 +202,8 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(c->shot_log.alloc(kShotLogCap));
 	CUDA_TRY(c->stats.alloc(1));
 	CUDA_TRY(c->rec.alloc(2 + kMaxSources));
-	CUDA_TRY(c->cand.alloc(world));
-	c->use_fast = c->use_dedup && !o.collect_stats && world == 1 && !o.per_shot_kernels;
+	c->use_fast = c->use_dedup && !o.collect_stats && !o.per_shot_kernels;
+	if (world > kMaxWorld) { set_error("world larger than 8"); return RADK_ERR_ARG; }
 	if (c->use_fast) {
 		// form-factor cache rows: 32 unless that would take more than a quarter of the free memory
 		size_t free_b = 0, total_b = 0;
@@ -230,6 +242,10 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		CUDA_TRY(c->handoff.alloc(1));
 		CUDA_TRY(c->partial.alloc(2 * (size_t)c->shots_ctas));
 		CUDA_TRY(c->budget.alloc(1));
+		CUDA_TRY(c->box.alloc(1));
+		CUDA_TRY(c->pred_round.alloc(1));
+		CUDA_TRY(c->fast_error.alloc(1));
+		CUDA_TRY(cudaMemsetAsync(c->box.p, 0, sizeof(PeerBox), st));
 		const int mask_words = (s->nnodes + 31) / 32;
 		CUDA_TRY(c->row_mask.alloc((size_t)kMaxRows * mask_words));
 		FastState &F = c->F;
@@ -238,6 +254,11 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.barrier = c->fast_uints.p + 1;
 		F.handoff = c->handoff.p, F.partial = c->partial.p, F.budget = c->budget.p;
 		F.row_mask = c->row_mask.p, F.mask_words = mask_words;
+		for (int t = 0; t < kMaxWorld; t++) F.box[t] = nullptr;
+		F.box[o.rank] = c->box.p;
+		F.rank = o.rank, F.world = world;
+		F.pred_round = c->pred_round.p, F.error = c->fast_error.p;
+		c->peers_connected = world == 1;
 		int rc2 = reset_fast_state(c);
 		if (rc2) return rc2;
 	}
@@ -247,7 +268,6 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), st));
 	CUDA_TRY(cudaMemsetAsync(c->stats.p, 0, sizeof(DevStats), st));
 	CUDA_TRY(cudaMemsetAsync(c->rec.p, 0, (2 + kMaxSources) * sizeof(ShooterRec), st));
-	CUDA_TRY(cudaMemsetAsync(c->cand.p, 0, world * sizeof(radk_candidate), st));
 
 	DevScene &S = c->S;
 	S.tree.cell_leaf = c->cell_leaf.p;
@@ -316,8 +336,12 @@ void launch_multi_source_iteration(radk_ctx *c) {
 int read_flags(radk_ctx *c) {
 	CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags.p, sizeof(*c->h_flags), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(c->h_shots, c->shots_done.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-	if (c->use_fast) CUDA_TRY(cudaMemcpyAsync(c->h_budget, c->budget.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+	if (c->use_fast) {
+		CUDA_TRY(cudaMemcpyAsync(c->h_budget, c->budget.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->h_error, c->fast_error.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	}
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if (c->use_fast && *c->h_error) { set_error("a peer rank did not answer within the device-side timeout"); return RADK_ERR_STATE; }
 	return RADK_OK;
 }
 
@@ -349,7 +373,8 @@ int radk_ctx_create(const radk_scene *s, const radk_opts *o, radk_ctx **out) {
 		    cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
 		    cudaMallocHost((void **)&c->h_flags, sizeof(*c->h_flags)) != cudaSuccess ||
 		    cudaMallocHost((void **)&c->h_shots, sizeof(long long)) != cudaSuccess ||
-		    cudaMallocHost((void **)&c->h_budget, sizeof(long long)) != cudaSuccess) {
+		    cudaMallocHost((void **)&c->h_budget, sizeof(long long)) != cudaSuccess ||
+		    cudaMallocHost((void **)&c->h_error, sizeof(int)) != cudaSuccess) {
 			set_error(std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()));
 			rc = RADK_ERR_CUDA;
 			break;
@@ -368,6 +393,8 @@ void radk_ctx_destroy(radk_ctx *c) {
 	if (c->h_flags) cudaFreeHost(c->h_flags);
 	if (c->h_shots) cudaFreeHost(c->h_shots);
 	if (c->h_budget) cudaFreeHost(c->h_budget);
+	if (c->h_error) cudaFreeHost(c->h_error);
+	for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -492,7 +519,10 @@ int radk_ctx_profile(radk_ctx *c, long long max_shots, double ms[3], long long n
 int radk_ctx_step(radk_ctx *c, long long max_shots, long long *shots_done, int *converged) {
 	if (!c) { set_error("radk_ctx_step: null context"); return RADK_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
+	if (c->opt.world > 1 && !c->use_fast) { set_error("multi-GPU contexts support the default (batched) path only"); return RADK_ERR_STATE; }
+	if (c->opt.world > 1 && !c->peers_connected) { set_error("radk_ctx_step: call radk_ctx_peer_connect first"); return RADK_ERR_STATE; }
 	long long before = 0;
+	if (c->h_error) *c->h_error = 0;
 	int rc = read_flags(c);
 	if (rc) return rc;
 	before = *c->h_shots;
@@ -654,8 +684,30 @@ double radk_ctx_device_ms(const radk_ctx *c) { return c ? c->device_ms : 0.0; }
 
 int radk_ctx_shoot(radk_ctx *c, const int *slots, int n) {
 	if (!c || !slots || n <= 0 || n > kMaxSources) { set_error("radk_ctx_shoot: bad argument"); return RADK_ERR_ARG; }
-	set_error("radk_ctx_shoot: not implemented yet");
-	return RADK_ERR_STATE;
+	if (c->opt.world > 1) { set_error("radk_ctx_shoot: single-GPU contexts only"); return RADK_ERR_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	std::vector<int> recv(n);
+	for (int j = 0; j < n; j++) {
+		if (slots[j] < 0 || slots[j] >= c->trinum || c->h_slot_to_recv[slots[j]] < 0) {
+			set_error("radk_ctx_shoot: slot is not a receiver (logical or out of range)");
+			return RADK_ERR_ARG;
+		}
+		recv[j] = c->h_slot_to_recv[slots[j]];
+	}
+	DevBuf<int> d;
+	CUDA_TRY(d.upload(recv, c->stream));
+	ShooterRec *list = c->rec.p + 2;
+	make_sources_kernel<<<1, kMaxSources, 0, c->stream>>>(c->S, d.p, n, list, 1);
+	const bool stats = c->opt.collect_stats != 0;
+	const int nb = blocks_for(c->R, 128);
+	if (stats) shade_receivers_kernel<true><<<nb, 128, 0, c->stream>>>(c->S, list, n);
+	else shade_receivers_kernel<false><<<nb, 128, 0, c->stream>>>(c->S, list, n);
+	after_generic_pass_kernel<<<1, 1, 0, c->stream>>>(c->S, list);
+	c->launches += 3;
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	c->have_current = false;
+	return RADK_OK;
 }
 
 int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from, int n, int *hit) {
@@ -681,16 +733,87 @@ int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from
 
 int radk_vertex_ff(radk_ctx *c, int shooter, const int *receiver, const int *vertex, int n, float *ff) {
 	if (!c || !receiver || !vertex || !ff || n < 0) { set_error("radk_vertex_ff: bad argument"); return RADK_ERR_ARG; }
-	if (shooter < 0 || shooter >= c->trinum) { set_error("radk_vertex_ff: shooter slot out of range"); return RADK_ERR_ARG; }
-	set_error("radk_vertex_ff: not implemented yet");
-	return RADK_ERR_STATE;
+	if (shooter < 0 || shooter >= c->trinum || c->h_slot_to_recv[shooter] < 0) {
+		set_error("radk_vertex_ff: shooter slot is not a receiver of this context");
+		return RADK_ERR_ARG;
+	}
+	if (n == 0) return RADK_OK;
+	CUDA_TRY(cudaSetDevice(c->device));
+	std::vector<int> recv(n), vert(n), src(1, c->h_slot_to_recv[shooter]);
+	for (int i = 0; i < n; i++) {
+		if (vertex[i] < 0 || vertex[i] > 2 || receiver[i] < 0 || receiver[i] >= c->trinum) { set_error("radk_vertex_ff: bad (receiver, vertex) pair"); return RADK_ERR_ARG; }
+		recv[i] = c->h_slot_to_recv[receiver[i]], vert[i] = vertex[i];
+	}
+	DevBuf<int> dr, dv, ds;
+	DevBuf<float> df;
+	CUDA_TRY(dr.upload(recv, c->stream));
+	CUDA_TRY(dv.upload(vert, c->stream));
+	CUDA_TRY(ds.upload(src, c->stream));
+	CUDA_TRY(df.alloc(n));
+	ShooterRec *tmp = c->rec.p + 2 + kMaxSources - 1;
+	make_sources_kernel<<<1, 32, 0, c->stream>>>(c->S, ds.p, 1, tmp, 0);
+	vertex_ff_batch_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->S, tmp, dr.p, dv.p, n, df.p);
+	c->launches += 2;
+	CUDA_TRY(cudaMemcpyAsync(ff, df.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	return RADK_OK;
 }
 
-int radk_ctx_local_candidate(radk_ctx *c, radk_candidate *out) { (void)c; (void)out; set_error("not implemented yet"); return RADK_ERR_STATE; }
-int radk_ctx_shoot_candidate(radk_ctx *c, const radk_candidate *s) { (void)c; (void)s; set_error("not implemented yet"); return RADK_ERR_STATE; }
-int radk_ctx_candidate_buffer(radk_ctx *c, void **p, size_t *b) { (void)c; (void)p; (void)b; set_error("not implemented yet"); return RADK_ERR_STATE; }
-int radk_ctx_local_candidate_dev(radk_ctx *c, void *s) { (void)c; (void)s; set_error("not implemented yet"); return RADK_ERR_STATE; }
-int radk_ctx_shoot_gathered_dev(radk_ctx *c, void *s) { (void)c; (void)s; set_error("not implemented yet"); return RADK_ERR_STATE; }
-int radk_ctx_converged_flag(radk_ctx *c, int *conv) { (void)c; (void)conv; set_error("not implemented yet"); return RADK_ERR_STATE; }
+int radk_ctx_peer_handle(radk_ctx *c, void *handle) {
+	if (!c || !handle) { set_error("radk_ctx_peer_handle: null argument"); return RADK_ERR_ARG; }
+	if (!c->use_fast) { set_error("radk_ctx_peer_handle: context does not use the batched path"); return RADK_ERR_STATE; }
+	static_assert(sizeof(cudaIpcMemHandle_t) == RADK_PEER_HANDLE_BYTES, "handle size");
+	CUDA_TRY(cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	CUDA_TRY(cudaIpcGetMemHandle(&h, c->box.p));
+	memcpy(handle, &h, sizeof(h));
+	return RADK_OK;
+}
+
+int radk_ctx_peer_connect(radk_ctx *c, const void *handles, int world) {
+	if (!c || !handles || world != c->opt.world) { set_error("radk_ctx_peer_connect: bad argument"); return RADK_ERR_ARG; }
+	if (!c->use_fast) { set_error("radk_ctx_peer_connect: context does not use the batched path"); return RADK_ERR_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	for (int t = 0; t < world; t++) {
+		if (t == c->opt.rank) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *)handles + (size_t)t * RADK_PEER_HANDLE_BYTES, sizeof(h));
+		void *p = nullptr;
+		CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		c->ipc_opened.push_back(p);
+		c->F.box[t] = (PeerBox *)p;
+	}
+	c->peers_connected = true;
+	return RADK_OK;
+}
+
+int radk_ctx_peer_connect_local(radk_ctx *c, radk_ctx *const *peers, int world) {
+	if (!c || !peers || world != c->opt.world) { set_error("radk_ctx_peer_connect_local: bad argument"); return RADK_ERR_ARG; }
+	if (!c->use_fast) { set_error("radk_ctx_peer_connect_local: context does not use the batched path"); return RADK_ERR_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	for (int t = 0; t < world; t++) {
+		if (!peers[t] || peers[t]->opt.rank != t || peers[t]->opt.world != world || !peers[t]->use_fast) {
+			set_error("radk_ctx_peer_connect_local: peers[r] must be rank r of the same world");
+			return RADK_ERR_ARG;
+		}
+		if (peers[t]->device != c->device) {
+			cudaError_t e = cudaDeviceEnablePeerAccess(peers[t]->device, 0);
+			if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+			else if (e != cudaSuccess) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return RADK_ERR_CUDA; }
+		}
+		c->F.box[t] = peers[t]->box.p;
+	}
+	c->peers_connected = true;
+	return RADK_OK;
+}
+
+int radk_ctx_owned_slots(radk_ctx *c, int *slots, int cap, int *n) {
+	if (!c || !n) { set_error("radk_ctx_owned_slots: null argument"); return RADK_ERR_ARG; }
+	*n = c->R;
+	if (slots)
+		for (int r = 0; r < c->R && r < cap; r++) slots[r] = c->recv_slot[r];
+	return RADK_OK;
+}
 
 }  // extern "C"

@@ -41,7 +41,31 @@ struct Partial {		// one CTA's best candidate of a shot
 	int pad;
 };
 
+// ---- multi-GPU mailboxes (one PeerBox per rank, in that rank's HBM, mapped into every peer) ---------
+// Ranks exchange (a) per round: their local top candidates with full shooter records, (b) per shot:
+// their local best (key, deltaB).  Writers store the payload, __threadfence_system(), then a sequence
+// number (run epoch << 40 | round or shot number); readers spin on the sequence number in their OWN
+// box (local memory), so a wait costs one NVLink store latency.  Payload slots are double-buffered by
+// parity: a writer can be at most one round / one shot ahead of the slowest reader.
+constexpr int kMaxWorld = 8;
+struct PredCand {
+	unsigned long long key;
+	ShooterRec rec;
+	int pad[2];
+};
+struct PeerBox {
+	Partial shot[2][kMaxWorld];
+	unsigned long long shot_seq[2][kMaxWorld];
+	PredCand pred[2][kMaxWorld][kMaxRows];
+	unsigned long long pred_seq[2][kMaxWorld];
+};
+
 struct FastState {
+	PeerBox *box[kMaxWorld];	// box[r] = rank r's mailbox (peer-mapped); box[rank] is local
+	int rank, world;
+	unsigned long long epoch;	// run epoch (bumped by reset / rewind on every rank alike)
+	unsigned long long *pred_round;	// rounds predicted so far in this epoch (device)
+	int *error;			// set when a peer wait timed out
 	float2 *ff;			// [rows][U] cached form factors: .x toward half 0, .y toward half 1
 	int rows;			// cache capacity (<= kMaxRows)
 	int *row_slot;			// [rows] slot whose form factors the row holds, -1 free
@@ -59,6 +83,77 @@ struct FastState {
 	int mask_words;
 	int *stalled;			// 1: shots_kernel stopped on a cache miss
 };
+
+// Spin until *p == expected (p is in local memory, written by a peer).  Gives up after ~20 s of SM
+// clock so that a dead peer cannot hang the GPU; the caller then flags an error.
+__device__ __forceinline__ bool peer_wait(const unsigned long long *p, unsigned long long expected) {
+	const volatile unsigned long long *vp = (const volatile unsigned long long *)p;
+	const long long t0 = clock64();
+	unsigned spins = 0;
+	while (*vp != expected) {
+		if ((++spins & 0xfff) == 0 && clock64() - t0 > 40000000000ll) return false;
+	}
+	__threadfence_system();
+	return true;
+}
+__device__ __forceinline__ void peer_copy(void *dst, const void *src, int bytes) {	// 8-byte granules, volatile stores
+	volatile unsigned long long *d = (volatile unsigned long long *)dst;
+	const unsigned long long *q = (const unsigned long long *)src;
+	for (int i = 0; i < bytes / 8; i++) d[i] = q[i];
+}
+
+// Warp 0 of one CTA: rebuild the form-factor cache around the candidate keys top[0..rows) (descending,
+// 0 = none): rows whose slot is no longer a candidate are freed, candidates without a row get the free
+// rows in order; F.todo / *F.ntodo list the rows to fill.  Returns (in every lane) the number of new rows;
+// lane j's row is written to *my_row.
+__device__ int rebuild_cache(const FastState &F, const unsigned long long *top, int lane, int *my_row) {
+	const int rows = F.rows;
+	const unsigned long long key = lane < rows ? top[lane] : 0ull;
+	const bool valid = key != 0ull;
+	const int slot = (int)(key & 0xffffffffu);
+	int row = valid ? F.slot_row[slot] : -1;
+	unsigned keepmask = 0u;
+	for (int j = 0; j < 32; j++) {
+		const int rj = __shfl_sync(0xffffffffu, row, j);
+		if (rj >= 0) keepmask |= 1u << rj;
+	}
+	int held = lane < rows ? F.row_slot[lane] : 0;		// slot held by row `lane`
+	if (lane < rows && held >= 0 && !((keepmask >> lane) & 1u)) {
+		F.slot_row[held] = -1, F.row_slot[lane] = -1, held = -1;
+	}
+	const unsigned freemask = __ballot_sync(0xffffffffu, lane < rows && held < 0);
+	const bool need = valid && row < 0;
+	const unsigned needmask = __ballot_sync(0xffffffffu, need);
+	const int rank = __popc(needmask & ((1u << lane) - 1u));
+	const int nfree = __popc(freemask), nneed = __popc(needmask);
+	if (need && rank < nfree) {
+		row = (int)__fns(freemask, 0, rank + 1);
+		F.row_slot[row] = slot, F.slot_row[slot] = row, F.todo[rank] = row;
+	}
+	const int nt = nneed < nfree ? nneed : nfree;
+	if (lane == 0) *F.ntodo = nt;
+	*my_row = row;
+	return nt;
+}
+
+// Leaf masks of the new rows (all threads of the CTA): which leaves list the shooter's original triangle.
+__device__ void build_row_masks(const DevScene &S, const FastState &F, int nt) {
+	for (int t = 0; t < nt; t++) {
+		unsigned *mask = F.row_mask + (size_t)F.todo[t] * F.mask_words;
+		for (int w = threadIdx.x; w < F.mask_words; w += blockDim.x) mask[w] = 0u;
+	}
+	__syncthreads();
+	for (int t = 0; t < nt; t++) {
+		const int row = F.todo[t];
+		const int logsrc = F.rec[row].logsrc;
+		unsigned *mask = F.row_mask + (size_t)row * F.mask_words;
+		const int b = S.tree.tri_leaf_begin[logsrc], e = S.tree.tri_leaf_begin[logsrc + 1];
+		for (int k = b + threadIdx.x; k < e; k += blockDim.x) {
+			const int leaf = S.tree.tri_leaves[k];
+			atomicOr(&mask[leaf >> 5], 1u << (leaf & 31));
+		}
+	}
+}
 
 // ---- predict ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
@@ -100,46 +195,44 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		if (threadIdx.x == 0) top[it] = m;
 	}
 	__syncthreads();
+	if (F.world > 1) {
+		// multi-GPU: publish the local candidates (key + complete shooter record) to every rank; the cache is
+		// rebuilt by predict_merge_kernel from the union
+		if (threadIdx.x == 0) *F.ticket = 0u;
+		__shared__ unsigned long long s_round;
+		if (threadIdx.x == 0) s_round = ++(*F.pred_round);
+		__syncthreads();
+		const int par = (int)(s_round & 1ull);
+		if (threadIdx.x < rows) {
+			PredCand pc;
+			pc.key = top[threadIdx.x], pc.pad[0] = pc.pad[1] = 0;
+			if (pc.key != 0ull) build_shooter(S, S.slot_to_recv[(int)(pc.key & 0xffffffffu)], &pc.rec);
+			else pc.rec.valid = 0;
+			for (int t = 0; t < F.world; t++) peer_copy(&F.box[t]->pred[par][F.rank][threadIdx.x], &pc, (int)sizeof(PredCand));
+			__threadfence_system();
+		}
+		__syncthreads();
+		if (threadIdx.x < F.world)
+			*((volatile unsigned long long *)&F.box[threadIdx.x]->pred_seq[par][F.rank]) = (F.epoch << 40) | s_round;
+		return;
+	}
 	// ---- warp 0 rebuilds the cache around the candidates: lane j owns candidate j and row j
 	if (warp == 0) {
 		if (lane == 0) *F.ticket = 0u;
-		const unsigned long long key = lane < rows ? top[lane] : 0ull;
-		const bool valid = key != 0ull;
-		const int slot = (int)(key & 0xffffffffu);
-		int row = valid ? F.slot_row[slot] : -1;
-		// rows still wanted
-		unsigned keepmask = 0u;
-		for (int j = 0; j < 32; j++) {
-			const int rj = __shfl_sync(0xffffffffu, row, j);
-			if (rj >= 0) keepmask |= 1u << rj;
-		}
-		int held = lane < rows ? F.row_slot[lane] : 0;		// slot held by row `lane`
-		if (lane < rows && held >= 0 && !((keepmask >> lane) & 1u)) {
-			F.slot_row[held] = -1, F.row_slot[lane] = -1, held = -1;
-		}
-		const unsigned freemask = __ballot_sync(0xffffffffu, lane < rows && held < 0);
-		const bool need = valid && row < 0;
-		const unsigned needmask = __ballot_sync(0xffffffffu, need);
-		const int rank = __popc(needmask & ((1u << lane) - 1u));
-		const int nfree = __popc(freemask), nneed = __popc(needmask);
-		if (need && rank < nfree) {
-			row = (int)__fns(freemask, 0, rank + 1);
-			F.row_slot[row] = slot, F.slot_row[slot] = row, F.todo[rank] = row;
-		}
-		const int nt = nneed < nfree ? nneed : nfree;
+		int row;
+		const int nt = rebuild_cache(F, top, lane, &row);
 		if (lane == 0) {
-			*F.ntodo = nt;
 			s_ntodo = nt;
 			// the exact argmax (top[0]) is the next shooter
 			ShotRec h;
 			h.pad[0] = h.pad[1] = 0;
-			if (!valid) {
+			if (top[0] == 0ull) {
 				h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
 				*S.sel.converged = 1;
 			} else {
-				h.slot = slot;
+				h.slot = (int)(top[0] & 0xffffffffu);
 				h.row = row;
-				const int r = S.slot_to_recv[slot];
+				const int r = S.slot_to_recv[h.slot];
 				h.dB[0] = S.st[0][r].w, h.dB[1] = S.st[1][r].w, h.dB[2] = S.st[2][r].w;
 				h.valid = 1;
 			}
@@ -153,22 +246,86 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		const int row = F.todo[threadIdx.x];
 		build_shooter(S, S.slot_to_recv[F.row_slot[row]], &F.rec[row]);
 	}
-	// leaf masks of the new rows: which leaves list the shooter's original triangle
-	for (int t = 0; t < nt; t++) {
-		unsigned *mask = F.row_mask + (size_t)F.todo[t] * F.mask_words;
-		for (int w = threadIdx.x; w < F.mask_words; w += blockDim.x) mask[w] = 0u;
+	__syncthreads();
+	build_row_masks(S, F, nt);
+}
+
+// Multi-GPU second half of the prediction (one CTA of 256 threads): wait for every rank's candidates,
+// take the global top `rows`, rebuild the cache (identically on every rank), adopt the shooter records.
+__global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastState F) {
+	__shared__ unsigned long long wmax[2][8];
+	__shared__ unsigned long long top[kMaxRows];
+	__shared__ int top_src[kMaxRows];
+	__shared__ int s_ntodo, s_ok;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned long long round = *F.pred_round;
+	const int par = (int)(round & 1ull);
+	PeerBox *mine = F.box[F.rank];
+	if (threadIdx.x == 0) s_ok = 1;
+	__syncthreads();
+	if (threadIdx.x < F.world && !peer_wait(&mine->pred_seq[par][threadIdx.x], (F.epoch << 40) | round)) s_ok = 0;
+	__syncthreads();
+	if (!s_ok) {
+		if (threadIdx.x == 0) {
+			*F.error = 1, *F.ntodo = 0;
+			ShotRec h = {-1, -1, {0.f, 0.f, 0.f}, 0, {0, 0}};
+			*F.handoff = h;
+		}
+		return;
+	}
+	const int rows = F.rows;
+	// thread t owns candidate (src = t / 32, j = t % 32)
+	const int src = threadIdx.x >> 5, j = threadIdx.x & 31;
+	unsigned long long k0 = 0ull;
+	if (src < F.world && j < rows) k0 = *((volatile unsigned long long *)&mine->pred[par][src][j].key);
+	for (int it = 0; it < rows; it++) {
+		const unsigned long long wm = warp_max_u64(k0);
+		if (lane == 0) wmax[it & 1][warp] = wm;
+		__syncthreads();
+		const unsigned long long m = warp_max_u64(lane < 8 ? wmax[it & 1][lane] : 0ull);
+		if (m != 0ull && k0 == m) k0 = 0ull, top_src[it] = threadIdx.x;
+		if (threadIdx.x == 0) top[it] = m;
 	}
 	__syncthreads();
-	for (int t = 0; t < nt; t++) {
-		const int row = F.todo[t];
-		const int logsrc = __float_as_int(S.geo[0][S.slot_to_recv[F.row_slot[row]]].w);
-		unsigned *mask = F.row_mask + (size_t)row * F.mask_words;
-		const int b = S.tree.tri_leaf_begin[logsrc], e = S.tree.tri_leaf_begin[logsrc + 1];
-		for (int k = b + threadIdx.x; k < e; k += blockDim.x) {
-			const int leaf = S.tree.tri_leaves[k];
-			atomicOr(&mask[leaf >> 5], 1u << (leaf & 31));
+	if (warp == 0) {
+		int row;
+		const int nt = rebuild_cache(F, top, lane, &row);
+		if (lane == 0) {
+			s_ntodo = nt;
+			ShotRec h;
+			h.pad[0] = h.pad[1] = 0;
+			if (top[0] == 0ull) {
+				h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
+				*S.sel.converged = 1;
+			} else {
+				const PredCand *pc = &mine->pred[par][top_src[0] >> 5][top_src[0] & 31];
+				h.slot = (int)(top[0] & 0xffffffffu);
+				h.row = row;
+				h.dB[0] = *((volatile float *)&pc->rec.dB[0]), h.dB[1] = *((volatile float *)&pc->rec.dB[1]),
+				h.dB[2] = *((volatile float *)&pc->rec.dB[2]);
+				h.valid = 1;
+			}
+			*F.handoff = h;
+			*F.stalled = 0;
 		}
 	}
+	__syncthreads();
+	const int nt = s_ntodo;
+	// adopt the shooter records of the new rows from the mailbox (one warp per row, 4-byte granules)
+	for (int t = warp; t < nt; t += 8) {
+		const int row = F.todo[t];
+		const int slot = F.row_slot[row];
+		int which = -1;
+		for (int i = 0; i < rows; i++)
+			if ((int)(top[i] & 0xffffffffu) == slot && top[i] != 0ull) which = top_src[i];
+		const volatile int *from = (const volatile int *)&mine->pred[par][which >> 5][which & 31].rec;
+		int *to = (int *)&F.rec[row];
+		for (int w = lane; w < (int)(sizeof(ShooterRec) / 4); w += 32) to[w] = from[w];
+	}
+	__syncthreads();
+	if (threadIdx.x < nt) F.rec[F.todo[threadIdx.x]].recv = S.slot_to_recv[F.rec[F.todo[threadIdx.x]].slot];
+	__syncthreads();
+	build_row_masks(S, F, nt);
 }
 
 // ---- batched form factors -----------------------------------------------------------------------
@@ -368,6 +525,7 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 	}
 	__syncthreads();
 	long long budget = *F.budget;
+	const long long shots_before = *S.sel.shots_done;
 	unsigned epoch = 0;
 	int parity = 0;
 	long long done = 0;
@@ -426,9 +584,9 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			}
 		}
 		epoch++;
-		grid_barrier(F.barrier, epoch * (unsigned)nctas);
-		// every CTA reduces all partials the same way -> identical `cur` everywhere, no second barrier
-		{
+		if (F.world == 1) {
+			grid_barrier(F.barrier, epoch * (unsigned)nctas);
+			// every CTA reduces all partials the same way -> identical `cur` everywhere, no second barrier
 			unsigned long long k = 0ull;
 			int who = -1;
 			for (int b = threadIdx.x; b < nctas; b += kShotsBlock) {
@@ -446,21 +604,82 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			}
 			__syncthreads();
 			if (threadIdx.x == 0) {
-				if (blockIdx.x == 0) S.sel.shot_log[(*S.sel.shots_done + done) % S.sel.shot_log_cap] = shooter_slot;
-				ShotRec n;
-				n.pad[0] = n.pad[1] = 0;
-				if (m == 0ull) {
-					n.slot = -1, n.row = -1, n.dB[0] = n.dB[1] = n.dB[2] = 0.0f, n.valid = 0;
-				} else {
-					n.slot = (int)(m & 0xffffffffu);
-					n.row = F.slot_row[n.slot];
-					n.dB[0] = s_best.dB[0], n.dB[1] = s_best.dB[1], n.dB[2] = s_best.dB[2];
-					n.valid = 1;
+				if (m == 0ull) s_best.key = 0ull;
+			}
+		} else {
+			// multi-GPU: CTA 0 waits for the local CTAs, reduces their partials and mails the rank's best to every
+			// rank; every CTA (on every rank) then waits for all ranks' mail in its own box.
+			const unsigned long long seq = (F.epoch << 40) | (unsigned long long)(shots_before + done + 1);
+			__syncthreads();
+			if (threadIdx.x == 0) { __threadfence(); atomicAdd(F.barrier, 1u); }
+			if (blockIdx.x == 0) {
+				if (threadIdx.x == 0) {
+					while (*((volatile unsigned *)F.barrier) < epoch * (unsigned)nctas) { }
+					__threadfence();
 				}
-				cur = n;
+				__syncthreads();
+				unsigned long long k = 0ull;
+				int who = -1;
+				for (int b = threadIdx.x; b < nctas; b += kShotsBlock) {
+					const unsigned long long kb = __ldcg(&F.partial[parity * max_ctas + b].key);
+					if (kb > k) k = kb, who = b;
+				}
+				const unsigned long long m1 = warp_max_u64(k);
+				if (lane == 0) s_key[warp] = m1;
+				__syncthreads();
+				unsigned long long m = 0ull;
+				for (int w = 0; w < kShotsBlock / 32; w++) m = s_key[w] > m ? s_key[w] : m;
+				if (threadIdx.x == 0) s_best.key = 0ull, s_best.dB[0] = s_best.dB[1] = s_best.dB[2] = 0.0f, s_best.pad = 0;
+				__syncthreads();
+				if (m != 0ull && k == m) {
+					const Partial *p = &F.partial[parity * max_ctas + who];
+					s_best.key = m, s_best.dB[0] = __ldcg(&p->dB[0]), s_best.dB[1] = __ldcg(&p->dB[1]), s_best.dB[2] = __ldcg(&p->dB[2]);
+				}
+				__syncthreads();
+				if (threadIdx.x < F.world) {
+					PeerBox *dst = F.box[threadIdx.x];
+					peer_copy(&dst->shot[parity][F.rank], &s_best, (int)sizeof(Partial));
+					__threadfence_system();
+					*((volatile unsigned long long *)&dst->shot_seq[parity][F.rank]) = seq;
+				}
+			}
+			__shared__ int s_ok;
+			if (threadIdx.x == 0) s_ok = 1;
+			__syncthreads();
+			PeerBox *mine = F.box[F.rank];
+			if (threadIdx.x < F.world && !peer_wait(&mine->shot_seq[parity][threadIdx.x], seq)) s_ok = 0;
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				Partial best;
+				best.key = 0ull, best.dB[0] = best.dB[1] = best.dB[2] = 0.0f, best.pad = 0;
+				if (s_ok) {
+					for (int t = 0; t < F.world; t++) {
+						const volatile Partial *p = &mine->shot[parity][t];
+						const unsigned long long kk = p->key;
+						if (kk > best.key) best.key = kk, best.dB[0] = p->dB[0], best.dB[1] = p->dB[1], best.dB[2] = p->dB[2];
+					}
+				} else {
+					*F.error = 1;
+				}
+				s_best = best;
 			}
 			__syncthreads();
 		}
+		if (threadIdx.x == 0) {
+			if (blockIdx.x == 0) S.sel.shot_log[(shots_before + done) % S.sel.shot_log_cap] = shooter_slot;
+			ShotRec n;
+			n.pad[0] = n.pad[1] = 0;
+			if (s_best.key == 0ull) {
+				n.slot = -1, n.row = -1, n.dB[0] = n.dB[1] = n.dB[2] = 0.0f, n.valid = 0;
+			} else {
+				n.slot = (int)(s_best.key & 0xffffffffu);
+				n.row = F.slot_row[n.slot];
+				n.dB[0] = s_best.dB[0], n.dB[1] = s_best.dB[1], n.dB[2] = s_best.dB[2];
+				n.valid = 1;
+			}
+			cur = n;
+		}
+		__syncthreads();
 		done++, budget--, parity ^= 1;
 	}
 	if (RPT > 0) {	// write the resident state back

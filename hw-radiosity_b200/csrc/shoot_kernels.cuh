@@ -412,6 +412,16 @@ __global__ void after_generic_pass_kernel(DevScene S, const ShooterRec *list) {
 	atomicAdd(&S.stats->shots, 1ull);
 }
 
+// caller-chosen shooters (radk_ctx_shoot / radk_vertex_ff): K2 for each listed receiver
+__global__ void make_sources_kernel(DevScene S, const int *recv, int n, ShooterRec *list, int set_nsrc) {
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < n) {
+		if (recv[j] >= 0) build_shooter(S, recv[j], &list[j]);
+		else list[j].valid = 0;
+	}
+	if (j == 0 && set_nsrc) *S.sel.nsrc = n;
+}
+
 // ---- test / utility kernels ----------------------------------------------------------------------
 __global__ void ray_batch_kernel(DevTree T, const float *p, const float *v, const int *from, int n, int *hit) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;

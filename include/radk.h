@@ -200,29 +200,26 @@ int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from
  * against shooter slot `shooter`. */
 int radk_vertex_ff(radk_ctx *c, int shooter, const int *receiver, const int *vertex, int n, float *ff);
 
-/* ---- multi-GPU (one process per GPU; the caller's launcher provides the transport) -------- */
-/* Candidate record exchanged between ranks each shot. */
-typedef struct radk_candidate {
-	float delta;		/* (dB0+dB1)+dB2 */
-	int slot;		/* global slot index; -1 = no candidate */
-	float p[3][3], c[3], n[3], area, deltaB[3];
-	int parent;
-	int pad[2];
-} radk_candidate;		/* 24 x 4 = 96 bytes */
-
-/* Local top candidate of this rank's shard (device argmax, copied to host). */
-int radk_ctx_local_candidate(radk_ctx *c, radk_candidate *out);
-/* Shade this rank's shard with the globally chosen shooter, then zero it if owned here. */
-int radk_ctx_shoot_candidate(radk_ctx *c, const radk_candidate *shooter);
-/* Device-pointer variants for NCCL plumbing: a device buffer of `world` radk_candidate records;
- * radk_ctx_local_candidate_dev writes record [rank]; after the caller's all-gather,
- * radk_ctx_shoot_gathered_dev reduces the `world` records on the device (lexicographic max of
- * (delta, slot)), shades, and sets *converged_flag_dev (int, device) when no candidate exists.
- * Both only enqueue work on the stream given (cudaStream_t as void*). */
-int radk_ctx_candidate_buffer(radk_ctx *c, void **dev_ptr, size_t *bytes);
-int radk_ctx_local_candidate_dev(radk_ctx *c, void *stream);
-int radk_ctx_shoot_gathered_dev(radk_ctx *c, void *stream);
-int radk_ctx_converged_flag(radk_ctx *c, int *converged);
+/* ---- multi-GPU: one process per GPU, receivers sharded by opts.rank / opts.world -------------------
+ * Octree, occluders and per-original tables are replicated; each context owns a contiguous range of the
+ * sorted receivers.  The only exchange on the path is the shooter selection:
+ * per round the ranks' top candidates (with complete shooter records), per shot the ranks' best
+ * (unshot energy, slot).  Both go through peer-mapped mailboxes written with plain NVLink stores from
+ * inside the kernels; the host only has to introduce the ranks to each other once:
+ *   1. every rank calls radk_ctx_peer_handle and the launcher all-gathers the 64-byte handles
+ *      (torch.distributed / NCCL in hw-radiosity_b200/dist.py),
+ *   2. every rank calls radk_ctx_peer_connect with the world x 64 bytes.
+ * After that radk_ctx_step must be called by all ranks with the same arguments; every rank ends with
+ * the same shooter sequence and its own shard of the radiosity, bit-identical to a single-GPU run.
+ * reset / rewind must be called on all ranks alike.  A peer that stops responding makes radk_ctx_step
+ * fail with RADK_ERR_STATE after a device-side timeout instead of hanging. */
+#define RADK_PEER_HANDLE_BYTES 64
+int radk_ctx_peer_handle(radk_ctx *c, void *handle);
+int radk_ctx_peer_connect(radk_ctx *c, const void *handles, int world);
+/* Same-process variant (tests, single-process multi-GPU drivers): peers[r] is rank r's context. */
+int radk_ctx_peer_connect_local(radk_ctx *c, radk_ctx *const *peers, int world);
+/* Receivers owned by this context: slots[] gets their TriStore slot indices (cap entries at most). */
+int radk_ctx_owned_slots(radk_ctx *c, int *slots, int cap, int *n);
 
 #ifdef __cplusplus
 }

@@ -162,3 +162,81 @@ int emu_run(const radk_scene *s, float converge, int rank, int world, int shots,
 }
 
 }  // extern "C"
+
+// ---- experiment: how many cast rays start in a leaf with a guaranteed plane blocker? ----------------
+extern "C" int emu_start_block_stats(const radk_scene *s, int shooter_slot, long long *out) {
+	FlatScene F;
+	if (flatten_scene(s, 0, 1, F)) return 1;
+	const DevTree T = F.host_tree(s);
+	const int r = F.slot_to_recv[shooter_slot];
+	const float p[3][3] = {{F.geo[0][r].x, F.geo[0][r].y, F.geo[0][r].z}, {F.geo[1][r].x, F.geo[1][r].y, F.geo[1][r].z},
+			       {F.geo[2][r].x, F.geo[2][r].y, F.geo[2][r].z}};
+	const int parent = F.recv_parent[r];
+	const float4 pn = F.par_n[parent];
+	ShooterRec sh;
+	make_shooter(p, pn.x, pn.y, pn.z, pn.w, F.geo[2][r].w, 1, 1, 1, parent, shooter_slot, r, &sh);
+	std::vector<unsigned> mask((T.nnodes + 31) / 32, 0u);
+	for (int k = T.tri_leaf_begin[sh.logsrc]; k < T.tri_leaf_begin[sh.logsrc + 1]; k++)
+		mask[T.tri_leaves[k] >> 5] |= 1u << (T.tri_leaves[k] & 31);
+	const float ext = s->G1[0] - s->G0[0];
+	const double eps = 1e-4 * ext;
+	long long cast = 0, killed = 0, blocked = 0, first_leaf_blocked = 0;
+	for (int h = 0; h < 2; h++) {
+		const FFSample &smp = sh.half[h];
+		std::vector<char> sb(T.nnodes, 0);
+		for (int leaf = 0; leaf < T.nnodes; leaf++) {
+			if (F.leaf_list4[leaf] < 0 || ((mask[leaf >> 5] >> (leaf & 31)) & 1u)) continue;
+			const float4 lo = F.leaf_lo[leaf], hi = F.leaf_hi[leaf];
+			for (const int4 *l4 = &F.list4[F.leaf_list4[leaf]];; l4++) {
+				const int ids[4] = {l4->x, l4->y, l4->z, l4->w};
+				bool end = false;
+				for (int e = 0; e < 4 && !end; e++) {
+					if (ids[e] < 0) { end = true; break; }
+					if (!(ids[e] & kPlaneFlag)) continue;
+					const float4 *o = &F.occ[(size_t)(ids[e] & kIdMask) * OCC_STRIDE];
+					const double n[3] = {o[0].x, o[0].y, o[0].z}, c[3] = {o[0].w, o[1].x, o[1].y};
+					const double blo[3] = {lo.x, lo.y, lo.z}, bhi[3] = {hi.x, hi.y, hi.z};
+					double pmin = 0, pmax = 0;	// range of p.n over the cell box
+					for (int k = 0; k < 3; k++) {
+						pmin += n[k] > 0 ? n[k] * blo[k] : n[k] * bhi[k];
+						pmax += n[k] > 0 ? n[k] * bhi[k] : n[k] * blo[k];
+					}
+					const double d = c[0] * n[0] + c[1] * n[1] + c[2] * n[2];
+					const double sdot = smp.cx * n[0] + smp.cy * n[1] + smp.cz * n[2];
+					// both the plane and the sample strictly above, or both strictly below, the whole box
+					double hp_min, hp_max, hs_min, hs_max;
+					if (d > pmax && sdot > pmax) hp_min = d - pmax, hp_max = d - pmin, hs_min = sdot - pmax, hs_max = sdot - pmin;
+					else if (d < pmin && sdot < pmin) hp_min = pmin - d, hp_max = pmax - d, hs_min = pmin - sdot, hs_max = pmax - sdot;
+					else continue;
+					if (hp_min < eps || hs_min < eps) continue;
+					if (hp_min < 2.5e-4 * (hs_max + eps)) continue;
+					if (hp_max > 1e5 * hs_min) continue;
+					sb[leaf] = 1;
+				}
+				if (end || sb[leaf]) break;
+			}
+		}
+		for (int u = 0; u < F.U; u++) {
+			const float4 v = F.uv[u];
+			const int par = float_as_int_hd(v.w);
+			const float4 n4 = F.par_n[par];
+			float dx, dy, dz;
+			bool c;
+			ff_geom(smp, n4.x, n4.y, n4.z, n4.w, v.x, v.y, v.z, dx, dy, dz, c);
+			if (!c) continue;
+			cast++;
+			const int leaf = leaf_of<false>(T, v.x, v.y, v.z, nullptr);
+			const bool sees = ray_sees(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, par, sh.logsrc);
+			if (!sees) blocked++;
+			if (leaf >= 0 && sb[leaf]) {
+				killed++;
+				if (sees) return 2;	// the criterion must never kill a visible ray
+			}
+			if (leaf >= 0 && !((mask[leaf >> 5] >> (leaf & 31)) & 1u) && !sees) {
+				if (leaf_any_hit(T, F.leaf_list4[leaf], v.x, v.y, v.z, dx, dy, dz, par)) first_leaf_blocked++;
+			}
+		}
+	}
+	out[0] = cast, out[1] = blocked, out[2] = first_leaf_blocked, out[3] = killed;
+	return 0;
+}

@@ -219,6 +219,31 @@ def test_reset_reruns_identically(hr, models_dir):
         assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
 
 
-def test_receiver_shards_reproduce_single_gpu(hr, models_dir):
-    """world=2 shards on one device, driven with the single-GPU shooter: union == single-GPU state."""
-    pytest.skip("covered by tests/test_gpu_multi.py once radk_ctx_shoot_candidate is wired")
+def test_shoot_with_chosen_sources_matches_oracle(hr, po, models_dir):
+    m = hr.Model(str(models_dir / "sbox.tri"))
+    sc = oracle_scene(po, m)
+    ctx = hr.Context(m, per_shot_kernels=1)
+    leaves = np.nonzero(m.triangles["parent"] >= 0)[0]
+    lights = [int(i) for i in leaves if (m.triangles["deltaB"][i] > 0).any()]
+    for srcs in ([lights[0]], lights[1:4]):
+        sc.shot_with(srcs)
+        ctx.shoot(srcs)
+    assert_state_equal(ctx, sc)
+    with pytest.raises(hr.RadkError):
+        ctx.shoot([int(np.nonzero(m.triangles["parent"] < 0)[0][0])])   # logical slots cannot shoot
+
+
+def test_vertex_form_factors_match_oracle(hr, po, models_dir):
+    m = hr.Model(str(models_dir / "model3s.tri"))
+    sc = oracle_scene(po, m)
+    ctx = hr.Context(m)
+    tri = m.triangles
+    leaves = np.nonzero(tri["parent"] >= 0)[0]
+    shooter = int(sc.select()[0])
+    rng = np.random.default_rng(3)
+    recv = rng.choice(leaves, 3000)
+    vert = rng.integers(0, 3, len(recv))
+    got = ctx.vertex_ff(shooter, recv, vert)
+    want = np.array([sc.vertex_ff(shooter, int(r), tri["p"][r, v]) for r, v in zip(recv, vert)], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (want > 0).any()
