@@ -240,3 +240,108 @@ extern "C" int emu_start_block_stats(const radk_scene *s, int shooter_slot, long
 	out[0] = cast, out[1] = blocked, out[2] = first_leaf_blocked, out[3] = killed;
 	return 0;
 }
+
+// ---- stateful shard emulation for the world_size > 1 CPU tests (gloo) -------------------------------
+// Mirrors the device protocol: every rank offers its local best candidate (key + complete shooter
+// record), all ranks pick the maximum key, every rank applies that shot to its own shard.
+struct EmuShard {
+	FlatScene F;
+	DevTree T;
+	std::vector<float> ff0, ff1;
+	std::vector<unsigned> mask;
+};
+
+extern "C" void *emu_shard_open(const radk_scene *s, int rank, int world) {
+	EmuShard *e = new EmuShard();
+	if (flatten_scene(s, rank, world, e->F)) { delete e; return nullptr; }
+	e->T = e->F.host_tree(s);
+	e->ff0.resize(e->F.U), e->ff1.resize(e->F.U);
+	e->mask.resize((e->T.nnodes + 31) / 32);
+	return e;
+}
+extern "C" void emu_shard_close(void *h) { delete (EmuShard *)h; }
+extern "C" int emu_shard_sizes(void *h, int *R, int *U) { EmuShard *e = (EmuShard *)h; *R = e->F.R, *U = e->F.U; return 0; }
+
+// local argmax: *key = 0 when this shard has no candidate; rec = the candidate's shooter record
+extern "C" int emu_shard_best(void *h, float converge, unsigned long long *key, ShooterRec *rec) {
+	EmuShard *e = (EmuShard *)h;
+	FlatScene &F = e->F;
+	unsigned long long best = 0;
+	for (int r = 0; r < F.R; r++) {
+		const float delta = F.st[0][r].w + F.st[1][r].w + F.st[2][r].w;
+		if (!(delta > converge)) continue;
+		const unsigned long long k = ((unsigned long long)ordered_bits(delta) << 32) | (unsigned)F.recv_slot[r];
+		best = k > best ? k : best;
+	}
+	*key = best;
+	memset(rec, 0, sizeof(*rec));
+	if (!best) return 0;
+	const int r = F.slot_to_recv[(int)(best & 0xffffffffu)];
+	const float p[3][3] = {{F.geo[0][r].x, F.geo[0][r].y, F.geo[0][r].z}, {F.geo[1][r].x, F.geo[1][r].y, F.geo[1][r].z},
+			       {F.geo[2][r].x, F.geo[2][r].y, F.geo[2][r].z}};
+	const float4 pn = F.par_n[F.recv_parent[r]];
+	make_shooter(p, pn.x, pn.y, pn.z, pn.w, F.geo[2][r].w, F.st[0][r].w, F.st[1][r].w, F.st[2][r].w, F.recv_parent[r],
+		     F.recv_slot[r], r, rec);
+	return 0;
+}
+
+extern "C" int emu_shard_apply(void *h, const ShooterRec *shp) {
+	EmuShard *e = (EmuShard *)h;
+	FlatScene &F = e->F;
+	const DevTree &T = e->T;
+	const ShooterRec sh = *shp;
+	std::fill(e->mask.begin(), e->mask.end(), 0u);
+	for (int k = T.tri_leaf_begin[sh.logsrc]; k < T.tri_leaf_begin[sh.logsrc + 1]; k++)
+		e->mask[T.tri_leaves[k] >> 5] |= 1u << (T.tri_leaves[k] & 31);
+	for (int u = 0; u < F.U; u++) {
+		const float4 v = F.uv[u];
+		const int parent = float_as_int_hd(v.w);
+		const float4 pn = F.par_n[parent];
+		float out[2] = {0.0f, 0.0f};
+		const int nh = sh.splittable ? 2 : 1;
+		for (int hh = 0; hh < nh; hh++) {
+			const FFSample &smp = sh.splittable ? sh.half[hh] : sh.centre;
+			float dx, dy, dz;
+			bool cast;
+			const float ff = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, cast);
+			if (cast && ray_sees(T, e->mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc)) out[hh] = ff;
+		}
+		e->ff0[u] = out[0], e->ff1[u] = out[1];
+	}
+	for (int r = 0; r < F.R; r++) {
+		float4 &a0 = F.st[0][r], &a1 = F.st[1][r], &a2 = F.st[2][r];
+		if (F.recv_slot[r] == sh.slot) { a0.w = a1.w = a2.w = 0.0f; continue; }
+		if (!(a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
+		      a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f)) continue;
+		const int4 id = F.vid[r];
+		const int ids[3] = {id.x, id.y, id.z};
+		const float4 fk = F.par_fk[id.w];
+		const float lo[3] = {fk.x * sh.dB[0] / 3, fk.y * sh.dB[1] / 3, fk.z * sh.dB[2] / 3};
+		float dB[3] = {a0.w, a1.w, a2.w};
+		float4 *acc[3] = {&a0, &a1, &a2};
+		for (int v = 0; v < 3; v++) {
+			const float ff = e->ff0[ids[v]] + e->ff1[ids[v]];
+			float d;
+			d = lo[0] * ff; dB[0] += d; acc[v]->x += d;
+			d = lo[1] * ff; dB[1] += d; acc[v]->y += d;
+			d = lo[2] * ff; dB[2] += d; acc[v]->z += d;
+		}
+		a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
+	}
+	return 0;
+}
+
+// owned slots and their state: slots[R], accB[R][9], deltaB[R][3]
+extern "C" int emu_shard_state(void *h, int *slots, float *accB, float *deltaB) {
+	EmuShard *e = (EmuShard *)h;
+	FlatScene &F = e->F;
+	for (int r = 0; r < F.R; r++) {
+		slots[r] = F.recv_slot[r];
+		for (int v = 0; v < 3; v++) {
+			accB[r * 9 + v * 3 + 0] = F.st[v][r].x, accB[r * 9 + v * 3 + 1] = F.st[v][r].y, accB[r * 9 + v * 3 + 2] = F.st[v][r].z;
+			deltaB[r * 3 + v] = F.st[v][r].w;
+		}
+	}
+	return 0;
+}
+extern "C" int emu_shooter_rec_bytes(void) { return (int)sizeof(ShooterRec); }
