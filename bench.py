@@ -29,15 +29,24 @@ WORKLOADS = {
     "room": ("room", {}, {}, "model/room.tri -converge 1200 -delta_ff 0.000005, first 200 shots"),
     "box": ("box", {}, {}, "model/box.tri default options, first 500 shots"),
     "blocks": ("blocks", {}, {}, "model/blocks.tri frozen mesh, to convergence"),
+    # seeded synthetic rooms (hw-radiosity_b200/synth.py), refined with the exhaustive PrePartition variant
+    "synth1m": ("synth:700000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {},
+                "synthetic room, seed 1, ~1.0 M receivers, first 200 shots"),
+    "synth10m": ("synth:6800000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {},
+                 "synthetic room, seed 1, ~10 M receivers, fixed 1000 shots"),
 }
-SHOT_CAP = {"room": 200, "box": 500}
+SHOT_CAP = {"room": 200, "box": 500, "synth1m": 200, "synth10m": 1000}
 ALGO_BYTES_PER_RECEIVER = 160
 
 
 def unpack_model(name, tmp):
-    path = os.path.join(tmp, name + ".tri")
+    path = os.path.join(tmp, name.replace(":", "_") + ".tri")
     with open(path, "wb") as f:
-        f.write(gzip.open(os.path.join(ROOT, "tests", "golden", "models", name + ".tri.gz")).read())
+        if name.startswith("synth:"):
+            from hw_radiosity_b200 import synth
+            f.write(synth.room_scene(int(name.split(":")[1]), seed=1))
+        else:
+            f.write(gzip.open(os.path.join(ROOT, "tests", "golden", "models", name + ".tri.gz")).read())
     return path
 
 
@@ -117,35 +126,54 @@ def cpu_reference_run(tri_path, shots, threads):
     return {"kind": "port", "rays": sc.stats["rays"], "seconds": dt, "shots": len(seq)}
 
 
+def cpu_port_run(model, shots, threads):
+    """Oracle port (oracle/radiosity_oracle.c, OpenMP) on a scene the reference's static limits cannot hold."""
+    from oracle import pyoracle as po
+    s = model.scene
+    sc = po.Scene(model.triangles.copy(), model.n0, model.nodes.copy(), model.tri_list.copy(), s.G0, s.G1, s.min_grid_len,
+                  s.grid_num, threads=threads)
+    t = time.perf_counter()
+    seq = sc.run(shots)
+    dt = time.perf_counter() - t
+    return {"kind": "port", "rays": sc.stats["rays"], "seconds": dt, "shots": len(seq)}
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation on this box's host cores, all threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    model, _, _, desc = WORKLOADS[args.workload]
+    model, mkw, _, desc = WORKLOADS[args.workload]
     with tempfile.TemporaryDirectory() as tmp:
         tri = unpack_model(model, tmp)
-        # bounded sample: size a step so that (steps + warmup) steps stay within ~3 minutes
-        probe = cpu_reference_run(tri, 10, threads)
+        if model.startswith("synth:"):
+            import hw_radiosity_b200 as hr                      # host front end only (no GPU needed)
+            mdl = hr.Model(tri, **mkw)
+            run = lambda shots: cpu_port_run(mdl, shots if shots else SHOT_CAP[args.workload], threads)
+        else:
+            run = lambda shots: cpu_reference_run(tri, shots, threads)
+        # bounded sample: size a step so that (steps + warmup) steps stay within ~2.5 minutes
+        probe = run(3 if model.startswith("synth:") else 10)
         per_shot = max(probe["seconds"] / max(probe["shots"], 1), 1e-6)
         total = SHOT_CAP.get(args.workload)
         budget = 150.0 / (args.steps + args.warmup)
-        shots = int(max(5, min(budget / per_shot, total or 10 ** 9)))
-        full = cpu_reference_run(tri, None, threads) if (total is None and budget / per_shot > 400) else None
-        if full is not None:
-            shots = None
+        shots = int(max(2, min(budget / per_shot, total or 10 ** 9)))
+        if total is None and budget / per_shot > 400:
+            shots = None                                        # the whole run fits: go to convergence
         for _ in range(args.warmup):
-            cpu_reference_run(tri, shots if shots else None, threads)
-        rays, secs, nshots = 0, 0.0, 0
+            run(shots)
+        rays, secs, nshots, kind = 0, 0.0, 0, "reference"
         for _ in range(args.steps):
-            r = cpu_reference_run(tri, shots if shots else None, threads)
+            r = run(shots)
             rays += r["rays"]; secs += r["seconds"]; nshots = r["shots"]; kind = r["kind"]
     value = rays / secs
-    sample = f"{model}.tri first {nshots} shots per step" if shots else f"{model}.tri to convergence ({nshots} shots) per step"
+    sample = f"{model} first {nshots} shots per step" if shots else f"{model} to convergence ({nshots} shots) per step"
     line = {
         "impl": "reference", "metric": "visibility_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "repo model (tests/golden/models, gzip of the reference's model/*.tri)",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "repo model (tests/golden/models, gzip of the reference's model/*.tri)" if not model.startswith("synth:") else "synthetic (seeded generator)",
         "config": {"workload": desc, "sample": sample, "threads": threads},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -157,33 +185,46 @@ def run_reference_arm(args):
 def run_ours(args):
     import torch
     import hw_radiosity_b200 as hr
+    from hw_radiosity_b200 import dist as rdist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    rank, world, local_rank = rdist.init("nccl")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
     model_name, mkw, ckw, desc = WORKLOADS[args.workload]
     cap = SHOT_CAP.get(args.workload, -1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     with tempfile.TemporaryDirectory() as tmp:
         tri = unpack_model(model_name, tmp)
         model = hr.Model(tri, **mkw)
+        # reference-equivalent ray count of one step (deterministic): one statistics run on rank 0, untimed
+        info = [None]
+        if rank == 0:
+            sctx = hr.Context(model, collect_stats=1, device=local_rank, **ckw)
+            sctx.step(cap)
+            st = sctx.stats()
+            info[0] = st
+            sctx.close()
         if world > 1:
-            raise SystemExit("multi-GPU bench arm not wired in this revision")
-        # reference-equivalent ray count of one step (deterministic): one statistics run, untimed
-        sctx = hr.Context(model, collect_stats=1, device=local_rank, **ckw)
-        sctx.step(cap)
-        st = sctx.stats()
+            dist.broadcast_object_list(info, src=0)
+        st = info[0]
         rays_per_step, shots_per_step, recv_shaded = st["rays"], st["shots"], st["receivers"]
         walk = {k: st[k] for k in ("traced_rays", "leaf_visits", "descent_steps", "tri_tests", "tri_accepts", "visible", "calff")}
-        sctx.close()
 
-        ctx = hr.Context(model, device=local_rank, **ckw)
+        ctx = rdist.sharded_context(model, rank, world, local_rank, **ckw)
         sizes = ctx.sizes()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
@@ -191,47 +232,58 @@ def run_ours(args):
             ctx.rewind()
             flush.fill_(rank + 1)
             torch.cuda.synchronize()
+            barrier()
             before = ctx.device_ms
             done, conv = ctx.step(cap)
             assert done == shots_per_step, (done, shots_per_step)
-            return ctx.device_ms - before
+            return max_over_ranks(ctx.device_ms - before)       # device time, max over ranks
 
         for _ in range(max(args.warmup, 3)):
             one_step()
         l0 = ctx.stats()["kernel_launches"]
         torch.cuda.synchronize()
+        barrier()
         with ClockSampler(local_rank) as clk:
             t0 = time.perf_counter()
             dev_ms = [one_step() for _ in range(args.steps)]
             torch.cuda.synchronize()
+            barrier()
             wall = time.perf_counter() - t0
         launches = ctx.stats()["kernel_launches"] - l0
         ms_per_step = sum(dev_ms) / len(dev_ms)
         value = rays_per_step / (ms_per_step / 1e3)
 
-        # per-kernel durations, live, CUDA events on the launching stream (first shots of a fresh run)
+        # per-kernel-class durations, live, CUDA events on the launching stream (collective: all ranks launch alike)
         ctx.rewind()
         flush.fill_(7)
         torch.cuda.synchronize()
+        barrier()
         kt = ctx.profile(cap)
         ctx.rewind()
 
         # end-to-end through the C ABI with host buffers: state upload + loop + download
         def e2e_step():
+            barrier()
             t = time.perf_counter()
-            ctx.reset(model)                 # H2D: accB/deltaB of every receiver from the host TriStore image
+            ctx.reset(model)                 # H2D: accB/deltaB of this rank's receivers from the host TriStore image
             ctx.step(cap)
-            ctx.download()                   # D2H: accB/deltaB of every receiver
-            return time.perf_counter() - t
+            ctx.download()                   # D2H: accB/deltaB of this rank's receivers
+            return max_over_ranks(time.perf_counter() - t)
         for _ in range(2):
             e2e_step()
         e2e_s = sum(e2e_step() for _ in range(args.steps)) / args.steps
         state_bytes = sizes["receivers"] * 48
 
-        # CPU baseline on this box's host cores (rank 0, N=1): the unmodified reference, bounded sample
+        # CPU baseline on this box's host cores (rank 0, N=1 only): the unmodified reference, bounded sample
+        cpu = None
         threads = os.cpu_count() or 1
-        cpu_shots = None if args.workload in ("church", "blocks") else min(cap, 40)
-        cpu = cpu_reference_run(tri, cpu_shots, threads)
+        if rank == 0 and world == 1:
+            if model_name.startswith("synth:"):
+                cpu = cpu_port_run(model, min(cap, 3), threads)          # the reference's MaxTri cannot hold this scene
+            else:
+                cpu_shots = None if args.workload in ("church", "blocks") else min(cap, 40)
+                cpu = cpu_reference_run(tri, cpu_shots, threads)
+        barrier()
 
     hbm_gbs, peak_src, sm_max = measured_peaks()
     # dominant kernel: the visibility / form-factor kernel (K3a: ff_batch_kernel).  Algorithmic bytes per launch =
@@ -249,9 +301,11 @@ def run_ours(args):
     p_fp32 = 148 * 128 * 2 * sm_max * 1e6
     line = {
         "metric": "visibility_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "repo model (tests/golden/models, gzip of the reference's model/*.tri)",
-        "config": {"workload": desc, "receivers": sizes["receivers"], "unique_vertices": sizes["unique_vertices"],
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32",
+        "data": "repo model (tests/golden/models, gzip of the reference's model/*.tri)" if not model_name.startswith("synth:") else "synthetic (seeded generator)",
+        "config": {"workload": desc, "receivers_per_rank": sizes["receivers"], "unique_vertices_per_rank": sizes["unique_vertices"],
+                   "parallelism": f"receiver shards x{world}" if world > 1 else "single GPU",
                    "shots_per_step": shots_per_step, "reference_equivalent_rays_per_step": rays_per_step,
                    "traced_rays_per_step": walk["traced_rays"], "l2": "flushed between steps (256 MiB write), state rewound on device",
                    "timing": "per-step CUDA-event windows around radk_ctx_step on its stream, mean of K steps",
@@ -274,10 +328,11 @@ def run_ours(args):
                           "frac": max(ALGO_BYTES_PER_RECEIVER * recv_per_shot / (hbm_gbs * 1e9), flops / max(shots_per_step, 1) / p_fp32) / (ms_per_step * 1e-3 / max(shots_per_step, 1))},
         "fp32": {"flops_per_step_counted": flops, "achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
                  "peak_tflops": p_fp32 / 1e12, "frac": flops / (ms_per_step * 1e-3) / p_fp32},
-        "cpu_baseline": {"value": cpu["rays"] / cpu["seconds"], "unit": "rays/s", "cores": threads, "kind": cpu["kind"],
-                         "sample": f"{model_name}.tri, {cpu['shots']} shots, shot loop only ({cpu['seconds']:.2f} s)",
-                         "seconds": cpu["seconds"]},
     }
+    if cpu is not None:
+        line["cpu_baseline"] = {"value": cpu["rays"] / cpu["seconds"], "unit": "rays/s", "cores": threads, "kind": cpu["kind"],
+                                "sample": f"{model_name}, {cpu['shots']} shots, shot loop only ({cpu['seconds']:.2f} s)",
+                                "seconds": cpu["seconds"]}
     if rank == 0:
         print(json.dumps(line))
 

@@ -159,7 +159,7 @@ class Model:
         L = load_library()
         mo = ModelOpts()
         L.radk_default_model_opts(C.byref(mo))
-        mo.light_scale, mo.tri_limit, mo.prepartition, mo.sample_area = light, tri_limit, int(prepartition), sample_area
+        mo.light_scale, mo.tri_limit, mo.prepartition, mo.sample_area = light, tri_limit, int(prepartition), sample_area   # prepartition: 0/1/2
         if max_tri:
             mo.max_tri = max_tri
         if max_tree_nodes:

@@ -153,9 +153,11 @@ void prepartition(Model &m) {
 		std::pair<float, int> top = *work.rbegin();
 		work.erase(top);
 		const int slot = top.second;
-		if (m.tri[slot].area < 1) break;
+		// opts.prepartition == 2 (synthetic scaling scenes only): keep going where the reference gives up
+		const bool exhaustive = m.opts.prepartition == 2;
+		if (m.tri[slot].area < 1) { if (exhaustive) continue; break; }
 		int child[4];
-		if (sp.split(slot, child) < 0) break;
+		if (sp.split(slot, child) < 0) { if (exhaustive && !sp.pool_full(4)) continue; break; }
 		if (is_light(m.tri[slot])) {	// shade.cpp:580-590
 			const radk_triangle &t = m.tri[slot];
 			for (int i = 0; i < 4; i++) {

@@ -120,7 +120,9 @@ typedef struct radk_model_opts {
 	int tri_limit;		/* -triangle */
 	int max_tri;		/* 0 = 1000000 */
 	int max_tree_nodes;	/* 0 = 20000 (rad.h:11) */
-	int prepartition;	/* 1 = run PrePartitionTriangles (shipped config) */
+	int prepartition;	/* 1 = run PrePartitionTriangles as the reference does (shipped config); 0 = skip;
+				 * 2 = exhaustive variant for synthetic scaling scenes: stale work-set entries and
+				 *     refused splits are skipped instead of ending the refinement (NOT reference behaviour) */
 	float sample_area;	/* <0: maxarea/100 (rad.cpp:337-338) */
 	int reserved[6];
 } radk_model_opts;
