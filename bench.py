@@ -334,7 +334,11 @@ def run_ours(args):
                                 "sample": f"{model_name}, {cpu['shots']} shots, shot loop only ({cpu['seconds']:.2f} s)",
                                 "seconds": cpu["seconds"]}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
