@@ -30,10 +30,11 @@ WORKLOADS = {
     "box": ("box", {}, {}, "model/box.tri default options, first 500 shots"),
     "blocks": ("blocks", {}, {}, "model/blocks.tri frozen mesh, to convergence"),
     # seeded synthetic rooms (hw-radiosity_b200/synth.py), refined with the exhaustive PrePartition variant
-    "synth1m": ("synth:700000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {},
-                "synthetic room, seed 1, ~1.0 M receivers, first 200 shots"),
-    "synth10m": ("synth:6800000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {},
-                 "synthetic room, seed 1, ~10 M receivers, fixed 1000 shots"),
+    # -converge 1 keeps candidates alive for the fixed shot count (the small ceiling light alone would end after 2 shots)
+    "synth1m": ("synth:700000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {"converge": 1.0},
+                "synthetic room, seed 1, ~1.4 M receivers, -converge 1, first 200 shots"),
+    "synth10m": ("synth:4800000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {"converge": 1.0},
+                 "synthetic room, seed 1, ~10 M receivers, -converge 1, fixed 1000 shots"),
 }
 SHOT_CAP = {"room": 200, "box": 500, "synth1m": 200, "synth10m": 1000}
 ALGO_BYTES_PER_RECEIVER = 160
@@ -126,12 +127,12 @@ def cpu_reference_run(tri_path, shots, threads):
     return {"kind": "port", "rays": sc.stats["rays"], "seconds": dt, "shots": len(seq)}
 
 
-def cpu_port_run(model, shots, threads):
+def cpu_port_run(model, shots, threads, converge=1200.0):
     """Oracle port (oracle/radiosity_oracle.c, OpenMP) on a scene the reference's static limits cannot hold."""
     from oracle import pyoracle as po
     s = model.scene
     sc = po.Scene(model.triangles.copy(), model.n0, model.nodes.copy(), model.tri_list.copy(), s.G0, s.G1, s.min_grid_len,
-                  s.grid_num, threads=threads)
+                  s.grid_num, threads=threads, converge=converge)
     t = time.perf_counter()
     seq = sc.run(shots)
     dt = time.perf_counter() - t
@@ -144,13 +145,13 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    model, mkw, _, desc = WORKLOADS[args.workload]
+    model, mkw, ckw, desc = WORKLOADS[args.workload]
     with tempfile.TemporaryDirectory() as tmp:
         tri = unpack_model(model, tmp)
         if model.startswith("synth:"):
             import hw_radiosity_b200 as hr                      # host front end only (no GPU needed)
             mdl = hr.Model(tri, **mkw)
-            run = lambda shots: cpu_port_run(mdl, shots if shots else SHOT_CAP[args.workload], threads)
+            run = lambda shots: cpu_port_run(mdl, shots if shots else SHOT_CAP[args.workload], threads, ckw.get("converge", 1200.0))
         else:
             run = lambda shots: cpu_reference_run(tri, shots, threads)
         # bounded sample: size a step so that (steps + warmup) steps stay within ~2.5 minutes
@@ -189,6 +190,7 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     rank, world, local_rank = rdist.init("nccl")
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -279,7 +281,7 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         if rank == 0 and world == 1:
             if model_name.startswith("synth:"):
-                cpu = cpu_port_run(model, min(cap, 3), threads)          # the reference's MaxTri cannot hold this scene
+                cpu = cpu_port_run(model, min(cap, 3), threads, ckw.get("converge", 1200.0))   # the reference's MaxTri cannot hold this scene
             else:
                 cpu_shots = None if args.workload in ("church", "blocks") else min(cap, 40)
                 cpu = cpu_reference_run(tri, cpu_shots, threads)

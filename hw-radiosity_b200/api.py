@@ -124,6 +124,7 @@ def load_library():
     L.radk_ctx_shooter_log.argtypes = [vp, ip, C.c_int, C.POINTER(C.c_longlong)]
     L.radk_ctx_trinum.argtypes = [vp]
     L.radk_ctx_download.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.radk_ctx_download_triangles.argtypes = [vp, vp, C.c_int, ip]
     L.radk_ctx_snapshot_colors.argtypes = [vp, vp, C.c_int]
     L.radk_ctx_stats.argtypes = [vp, C.POINTER(Stats)]
     L.radk_ctx_device_ms.argtypes = [vp]
@@ -298,6 +299,15 @@ class Context:
         parent = np.full(n, -1, dtype=np.int32)
         _check(load_library().radk_ctx_download(self._h, accB.ctypes.data, deltaB.ctypes.data, parent.ctypes.data, n))
         return accB, deltaB, parent
+
+    def download_triangles(self):
+        """Adaptive-split contexts: the whole (grown) TriStore as 236-byte records."""
+        n = C.c_int()
+        L = load_library()
+        _check(L.radk_ctx_download_triangles(self._h, None, 0, C.byref(n)))
+        tri = np.zeros(n.value, dtype=TRI_DTYPE)
+        _check(L.radk_ctx_download_triangles(self._h, tri.ctypes.data, n.value, C.byref(n)))
+        return tri
 
     def download_into(self, model):
         """Merge the device radiosity back into the model's slots (for the .fin writer)."""

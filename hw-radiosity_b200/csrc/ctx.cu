@@ -16,6 +16,7 @@
 #include "radk.h"
 #include "shoot_kernels.cuh"
 #include "fast_kernels.cuh"
+#include "split_kernels.cuh"
 #include "scene_flatten.hpp"
 
 namespace radk {
@@ -108,6 +109,14 @@ struct radk_ctx {
 	struct HostFlags { int ncand, nsrc, converged; } *h_flags = nullptr;	// pinned
 	long long *h_shots = nullptr;		// pinned
 	bool use_dedup = true;
+	// adaptive-split mode (split_kernels.cuh): slot-indexed pool instead of the sorted receiver planes
+	bool split_mode = false;
+	SplitScene SP{};
+	DevBuf<float4> sp_p[3], sp_n, sp_st[3], sp_fk, sp_ffs;
+	DevBuf<radk_triangle> sp_rec;
+	DevBuf<int> sp_count, sp_bsum, sp_boff, sp_trinum, sp_growth;
+	int sp_host_trinum = 0;
+	unsigned long long sp_shot_no = 0;
 };
 
 namespace {
@@ -149,6 +158,153 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	CUDA_TRY(cudaLaunchCooperativeKernel(c->shots_fn, dim3((unsigned)c->shots_ctas), dim3(kShotsBlock), args, 0, st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
 	c->launches += 3;
+	return RADK_OK;
+}
+
+// ---- adaptive-split mode -----------------------------------------------------------------------------
+int upload_split_scene(radk_ctx *c, const radk_scene *s) {
+	const radk_opts &o = c->opt;
+	cudaStream_t st = c->stream;
+	c->split_mode = true;
+	c->use_dedup = false, c->use_fast = false;
+	c->n0 = s->n0;
+	const int max_tri = o.max_tri > 0 ? o.max_tri : 1000000;
+	const int limit = std::min(max_tri, o.tri_limit);
+	if (s->trinum > limit) { set_error("scene larger than the triangle limit"); return RADK_ERR_ARG; }
+	const int cap = limit;
+	FlatScene F;
+	radk_scene empty = *s;
+	empty.trinum = 0;		// only the octree / occluder part of the flattening is needed
+	const int frc = flatten_scene(&empty, 0, 1, F);
+	if (frc != RADK_OK) { set_error(F.error); return frc; }
+	CUDA_TRY(c->cell_leaf.upload(F.cell_leaf, st));
+	CUDA_TRY(c->leaf_lo.upload(F.leaf_lo, st));
+	CUDA_TRY(c->leaf_hi.upload(F.leaf_hi, st));
+	CUDA_TRY(c->list.upload(F.list, st));
+	CUDA_TRY(c->list4.upload(F.list4, st));
+	CUDA_TRY(c->leaf_list4.upload(F.leaf_list4, st));
+	CUDA_TRY(c->tri_leaf_begin.upload(F.tri_leaf_begin, st));
+	CUDA_TRY(c->tri_leaves.upload(F.tri_leaves, st));
+	CUDA_TRY(c->occ.upload(F.occ, st));
+	std::vector<float4> p[3], stt[3], nn(cap), fk(cap);
+	for (int v = 0; v < 3; v++) p[v].assign(cap, make_float4(0, 0, 0, 0)), stt[v].assign(cap, make_float4(0, 0, 0, 0));
+	std::vector<radk_triangle> rec(cap);
+	memset(rec.data(), 0, sizeof(radk_triangle) * (size_t)cap);
+	const float kref = (float)(0.5 / 255.0);
+	for (int i = 0; i < cap; i++) p[0][i].w = flat_detail::ibits(-1);
+	for (int i = 0; i < s->trinum; i++) {
+		const radk_triangle &t = s->tri[i];
+		rec[i] = t;
+		p[0][i] = make_float4(t.p[0][0], t.p[0][1], t.p[0][2], flat_detail::ibits(t.parent));
+		p[1][i] = make_float4(t.p[1][0], t.p[1][1], t.p[1][2], t.area);
+		p[2][i] = make_float4(t.p[2][0], t.p[2][1], t.p[2][2], 0.f);
+		nn[i] = make_float4(t.n[0], t.n[1], t.n[2], sqrtf(t.n[0] * t.n[0] + t.n[1] * t.n[1] + t.n[2] * t.n[2]));
+		fk[i] = make_float4(t.Frgb[0] * kref, t.Frgb[1] * kref, t.Frgb[2] * kref, 0.f);
+		for (int v = 0; v < 3; v++) stt[v][i] = make_float4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
+	}
+	for (int v = 0; v < 3; v++) {
+		CUDA_TRY(c->sp_p[v].upload(p[v], st));
+		CUDA_TRY(c->sp_st[v].upload(stt[v], st));
+	}
+	CUDA_TRY(c->sp_n.upload(nn, st));
+	CUDA_TRY(c->sp_fk.upload(fk, st));
+	CUDA_TRY(c->sp_rec.upload(rec, st));
+	CUDA_TRY(c->sp_ffs.alloc(cap));
+	CUDA_TRY(c->sp_count.alloc(cap));
+	const int maxblocks = (cap + kScanBlock - 1) / kScanBlock;
+	CUDA_TRY(c->sp_bsum.alloc(maxblocks));
+	CUDA_TRY(c->sp_boff.alloc(maxblocks));
+	CUDA_TRY(c->sp_trinum.alloc(1));
+	CUDA_TRY(c->sp_growth.alloc(1));
+	CUDA_TRY(cudaMemsetAsync(c->sp_count.p, 0, (size_t)cap * sizeof(int), st));
+	c->sp_host_trinum = s->trinum;
+	c->trinum = s->trinum;
+	CUDA_TRY(cudaMemcpyAsync(c->sp_trinum.p, &c->sp_host_trinum, sizeof(int), cudaMemcpyHostToDevice, st));
+	c->max_blocks = std::max(1, std::min((cap + 255) / 256, 4 * 148));
+	CUDA_TRY(c->partial_key.alloc(c->max_blocks));
+	CUDA_TRY(c->partial_cnt.alloc(c->max_blocks));
+	CUDA_TRY(c->ticket.alloc(1));
+	CUDA_TRY(c->bound.alloc(1));
+	CUDA_TRY(c->flags.alloc(4));
+	CUDA_TRY(c->shots_done.alloc(1));
+	CUDA_TRY(c->shot_log.alloc(kShotLogCap));
+	CUDA_TRY(c->stats.alloc(1));
+	CUDA_TRY(c->rec.alloc(2 + kMaxSources));
+	CUDA_TRY(cudaMemsetAsync(c->ticket.p, 0, sizeof(unsigned), st));
+	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->stats.p, 0, sizeof(DevStats), st));
+	CUDA_TRY(cudaMemsetAsync(c->rec.p, 0, (2 + kMaxSources) * sizeof(ShooterRec), st));
+	SplitScene &S = c->SP;
+	S.tree.cell_leaf = c->cell_leaf.p, S.tree.leaf_lo = c->leaf_lo.p, S.tree.leaf_hi = c->leaf_hi.p;
+	S.tree.list = c->list.p, S.tree.list4 = c->list4.p, S.tree.leaf_list4 = c->leaf_list4.p;
+	S.tree.tri_leaf_begin = c->tri_leaf_begin.p, S.tree.tri_leaves = c->tri_leaves.p, S.tree.occ = c->occ.p;
+	S.tree.nnodes = s->nnodes;
+	for (int k = 0; k < 3; k++) S.tree.G0[k] = s->G0[k], S.tree.G1[k] = s->G1[k];
+	S.tree.min_grid_len = s->min_grid_len, S.tree.grid_num = s->grid_num, S.tree.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
+	S.capacity = cap, S.limit = limit, S.trinum = c->sp_trinum.p;
+	for (int v = 0; v < 3; v++) S.p[v] = c->sp_p[v].p, S.st[v] = c->sp_st[v].p;
+	S.n = c->sp_n.p, S.fk = c->sp_fk.p, S.rec = c->sp_rec.p, S.count = c->sp_count.p, S.ffs = c->sp_ffs.p;
+	S.block_sum = c->sp_bsum.p, S.block_off = c->sp_boff.p;
+	S.converge = o.converge, S.area_limit = o.area_limit, S.sample_area = o.sample_area, S.delta_ff = o.delta_ff;
+	S.stats = c->stats.p;
+	S.sel.partial_key = c->partial_key.p, S.sel.partial_cnt = c->partial_cnt.p, S.sel.ticket = c->ticket.p;
+	S.sel.bound = c->bound.p;
+	S.sel.ncand = c->flags.p, S.sel.nsrc = c->flags.p + 1, S.sel.converged = c->flags.p + 2;
+	S.sel.shots_done = c->shots_done.p, S.sel.shot_log = c->shot_log.p, S.sel.shot_log_cap = kShotLogCap;
+	S.shot_no = 0;
+	if (!(o.sample_area > 0)) { set_error("adaptive splitting needs opts.sample_area > 0 (radk_model_sample_area)"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaStreamSynchronize(st));
+	return RADK_OK;
+}
+
+// one shot of the split-enabled loop (rad.cpp:406-451 with the do/while over the growing pool)
+int split_one_shot(radk_ctx *c, bool *converged) {
+	cudaStream_t st = c->stream;
+	ShooterRec *sh = c->rec.p;
+	split_select_kernel<<<c->max_blocks, 256, 0, st>>>(c->SP, sh);
+	c->launches++;
+	CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags.p, sizeof(*c->h_flags), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	if (c->h_flags->converged) { *converged = true; return RADK_OK; }
+	c->SP.shot_no = ++c->sp_shot_no;
+	int prev = 0, n = c->sp_host_trinum;
+	while (n > prev) {
+		const int count = n - prev;
+		const int nb = (count + kScanBlock - 1) / kScanBlock;
+		split_shade_kernel<<<(count + 127) / 128, 128, 0, st>>>(c->SP, sh, prev, n);
+		split_scan_sums_kernel<<<nb, kScanBlock, 0, st>>>(c->SP, prev, n);
+		split_scan_offsets_kernel<<<1, kScanBlock, 0, st>>>(c->SP, nb, c->sp_growth.p);
+		split_append_kernel<<<nb, kScanBlock, 0, st>>>(c->SP, sh, prev, n, n);
+		c->launches += 4;
+		int growth = 0;
+		CUDA_TRY(cudaMemcpyAsync(&growth, c->sp_growth.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		// splits are granted to a prefix of the requests (isFullPool is monotone): the pool grows by the
+		// requests that still fitted when their turn came
+		int grown = std::min(growth, std::max(0, c->SP.limit - 4 - n));
+		if (growth > 0 && grown < growth) {
+			// some requests were refused: the granted prefix ends where first + 4 >= limit; recompute exactly on the host
+			std::vector<int> cnt(count);
+			CUDA_TRY(cudaMemcpy(cnt.data(), c->sp_count.p + prev, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
+			int off = 0;
+			for (int k = 0; k < count; k++) {
+				if (cnt[k] == 0) continue;
+				if (n + off + 4 >= c->SP.limit) break;
+				off += cnt[k];
+			}
+			grown = off;
+		}
+		prev = n;
+		n += grown;
+		c->sp_host_trinum = n;
+		CUDA_TRY(cudaMemcpyAsync(c->sp_trinum.p, &c->sp_host_trinum, sizeof(int), cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	split_finish_shot_kernel<<<1, 1, 0, st>>>(c->SP, sh);
+	c->launches++;
+	c->trinum = c->sp_host_trinum;
+	*converged = false;
 	return RADK_OK;
 }
 
@@ -355,7 +511,7 @@ int radk_ctx_create(const radk_scene *s, const radk_opts *o, radk_ctx **out) {
 	if (o) opt = *o; else radk_default_opts(&opt);
 	if (opt.world <= 0) opt.world = 1;
 	if (opt.rank < 0 || opt.rank >= opt.world) { set_error("radk_ctx_create: rank outside [0, world)"); return RADK_ERR_ARG; }
-	if (opt.split_enabled) { set_error("radk_ctx_create: adaptive splitting is not available in this build"); return RADK_ERR_STATE; }
+	if (opt.split_enabled && opt.world > 1) { set_error("radk_ctx_create: adaptive splitting runs on one GPU"); return RADK_ERR_ARG; }
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
 	if (e != cudaSuccess || ndev == 0) {
@@ -379,7 +535,7 @@ int radk_ctx_create(const radk_scene *s, const radk_opts *o, radk_ctx **out) {
 			rc = RADK_ERR_CUDA;
 			break;
 		}
-		rc = upload_scene(c, s);
+		rc = opt.split_enabled ? upload_split_scene(c, s) : upload_scene(c, s);
 	} while (0);
 	if (rc != RADK_OK) { radk_ctx_destroy(c); return rc; }
 	*out = c;
@@ -402,6 +558,7 @@ void radk_ctx_destroy(radk_ctx *c) {
 }
 
 int radk_ctx_reset(radk_ctx *c, const radk_scene *s) {
+	if (c && c->split_mode) { set_error("radk_ctx_reset: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !s) { set_error("radk_ctx_reset: null argument"); return RADK_ERR_ARG; }
 	if (s->trinum != c->trinum) { set_error("radk_ctx_reset: scene size changed"); return RADK_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
@@ -426,6 +583,7 @@ int radk_ctx_reset(radk_ctx *c, const radk_scene *s) {
 }
 
 int radk_ctx_rewind(radk_ctx *c) {
+	if (c && c->split_mode) { set_error("radk_ctx_rewind: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c) { set_error("radk_ctx_rewind: null context"); return RADK_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
 	for (int v = 0; v < 3; v++)
@@ -448,6 +606,7 @@ int radk_ctx_sizes(const radk_ctx *c, int *receivers, int *unique_vertices, int 
 }
 
 int radk_ctx_profile(radk_ctx *c, long long max_shots, double ms[3], long long n[3], long long *shots) {
+	if (c && c->split_mode) { set_error("radk_ctx_profile: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !ms || !n) { set_error("radk_ctx_profile: bad argument"); return RADK_ERR_ARG; }
 	if (!c->use_dedup) { set_error("radk_ctx_profile: single-source contexts only"); return RADK_ERR_STATE; }
 	CUDA_TRY(cudaSetDevice(c->device));
@@ -529,7 +688,14 @@ int radk_ctx_step(radk_ctx *c, long long max_shots, long long *shots_done, int *
 	long long done = 0;
 	int conv = 0;
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-	if (c->use_fast) {
+	if (c->split_mode) {
+		while (max_shots < 0 || done < max_shots) {
+			bool cv = false;
+			if ((rc = split_one_shot(c, &cv))) return rc;
+			if (cv) { conv = 1; break; }
+			done++;
+		}
+	} else if (c->use_fast) {
 		*c->h_budget = max_shots < 0 ? (1ll << 60) : max_shots;
 		const long long budget0 = *c->h_budget;
 		CUDA_TRY(cudaMemcpyAsync(c->budget.p, c->h_budget, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
@@ -577,6 +743,7 @@ int radk_ctx_step(radk_ctx *c, long long max_shots, long long *shots_done, int *
 }
 
 int radk_ctx_select(radk_ctx *c, int *slots, int cap, int *n) {
+	if (c && c->split_mode) { set_error("radk_ctx_select: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !n) { set_error("radk_ctx_select: null argument"); return RADK_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
 	ShooterRec *list = c->rec.p + 2;
@@ -616,6 +783,27 @@ int radk_ctx_download(radk_ctx *c, float *accB, float *deltaB, int *parent, int 
 	if (!c) { set_error("radk_ctx_download: null context"); return RADK_ERR_ARG; }
 	if (trinum < c->trinum) { set_error("radk_ctx_download: buffers smaller than trinum"); return RADK_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
+	if (c->split_mode) {
+		const int n = c->trinum;
+		std::vector<float4> hs[3], hp(n);
+		for (int v = 0; v < 3; v++) {
+			hs[v].resize(n);
+			CUDA_TRY(cudaMemcpyAsync(hs[v].data(), c->sp_st[v].p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		}
+		CUDA_TRY(cudaMemcpyAsync(hp.data(), c->sp_p[0].p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		for (int i = 0; i < n; i++) {
+			int par;
+			memcpy(&par, &hp[i].w, 4);
+			if (parent) parent[i] = par;
+			if (par < 0) continue;
+			for (int v = 0; v < 3; v++) {
+				if (accB) accB[(size_t)i * 9 + v * 3] = hs[v][i].x, accB[(size_t)i * 9 + v * 3 + 1] = hs[v][i].y, accB[(size_t)i * 9 + v * 3 + 2] = hs[v][i].z;
+				if (deltaB) deltaB[(size_t)i * 3 + v] = hs[v][i].w;
+			}
+		}
+		return RADK_OK;
+	}
 	std::vector<float4> h[3];
 	for (int v = 0; v < 3; v++) {
 		h[v].resize(c->R);
@@ -638,13 +826,39 @@ int radk_ctx_download(radk_ctx *c, float *accB, float *deltaB, int *parent, int 
 }
 
 int radk_ctx_download_triangles(radk_ctx *c, radk_triangle *tri, int cap, int *trinum) {
-	(void)tri; (void)cap; (void)trinum;
-	if (!c) { set_error("radk_ctx_download_triangles: null context"); return RADK_ERR_ARG; }
-	set_error("radk_ctx_download_triangles: only meaningful for adaptive-split contexts");
-	return RADK_ERR_STATE;
+	if (!c || !trinum) { set_error("radk_ctx_download_triangles: null argument"); return RADK_ERR_ARG; }
+	if (!c->split_mode) { set_error("radk_ctx_download_triangles: only meaningful for adaptive-split contexts"); return RADK_ERR_STATE; }
+	*trinum = c->trinum;
+	if (!tri) return RADK_OK;
+	if (cap < c->trinum) { set_error("radk_ctx_download_triangles: buffer smaller than trinum"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	const int n = c->trinum;
+	std::vector<float4> hp[3], hs[3], hn(n);
+	for (int v = 0; v < 3; v++) {
+		hp[v].resize(n), hs[v].resize(n);
+		CUDA_TRY(cudaMemcpyAsync(hp[v].data(), c->sp_p[v].p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(hs[v].data(), c->sp_st[v].p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	}
+	CUDA_TRY(cudaMemcpyAsync(hn.data(), c->sp_n.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(tri, c->sp_rec.p, (size_t)n * sizeof(radk_triangle), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	for (int i = 0; i < n; i++) {
+		radk_triangle &t = tri[i];
+		for (int v = 0; v < 3; v++) {
+			t.p[v][0] = hp[v][i].x, t.p[v][1] = hp[v][i].y, t.p[v][2] = hp[v][i].z;
+			t.accB[v][0] = hs[v][i].x, t.accB[v][1] = hs[v][i].y, t.accB[v][2] = hs[v][i].z;
+			t.deltaB[v] = hs[v][i].w;
+		}
+		for (int k = 0; k < 3; k++) t.c[k] = (float)((double)(t.p[0][k] + t.p[1][k] + t.p[2][k]) / 3.0);
+		t.n[0] = hn[i].x, t.n[1] = hn[i].y, t.n[2] = hn[i].z;
+		t.area = hp[1][i].w;
+		memcpy(&t.parent, &hp[0][i].w, 4);
+	}
+	return RADK_OK;
 }
 
 int radk_ctx_snapshot_colors(radk_ctx *c, int *rgb, int trinum) {
+	if (c && c->split_mode) { set_error("radk_ctx_snapshot_colors: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !rgb) { set_error("radk_ctx_snapshot_colors: null argument"); return RADK_ERR_ARG; }
 	if (trinum < c->trinum) { set_error("radk_ctx_snapshot_colors: buffer smaller than trinum"); return RADK_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
@@ -683,6 +897,7 @@ int radk_ctx_stats(radk_ctx *c, radk_stats *out) {
 double radk_ctx_device_ms(const radk_ctx *c) { return c ? c->device_ms : 0.0; }
 
 int radk_ctx_shoot(radk_ctx *c, const int *slots, int n) {
+	if (c && c->split_mode) { set_error("radk_ctx_shoot: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !slots || n <= 0 || n > kMaxSources) { set_error("radk_ctx_shoot: bad argument"); return RADK_ERR_ARG; }
 	if (c->opt.world > 1) { set_error("radk_ctx_shoot: single-GPU contexts only"); return RADK_ERR_STATE; }
 	CUDA_TRY(cudaSetDevice(c->device));
@@ -723,7 +938,7 @@ int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from
 	CUDA_TRY(cudaMemcpyAsync(dp.p, p, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(dv.p, v, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(df.p, from, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-	ray_batch_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->S.tree, dp.p, dv.p, df.p, n, dh.p);
+	ray_batch_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->split_mode ? c->SP.tree : c->S.tree, dp.p, dv.p, df.p, n, dh.p);
 	c->launches++;
 	CUDA_TRY(cudaMemcpyAsync(hit, dh.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -732,6 +947,7 @@ int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from
 }
 
 int radk_vertex_ff(radk_ctx *c, int shooter, const int *receiver, const int *vertex, int n, float *ff) {
+	if (c && c->split_mode) { set_error("radk_vertex_ff: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !receiver || !vertex || !ff || n < 0) { set_error("radk_vertex_ff: bad argument"); return RADK_ERR_ARG; }
 	if (shooter < 0 || shooter >= c->trinum || c->h_slot_to_recv[shooter] < 0) {
 		set_error("radk_vertex_ff: shooter slot is not a receiver of this context");
@@ -761,6 +977,7 @@ int radk_vertex_ff(radk_ctx *c, int shooter, const int *receiver, const int *ver
 }
 
 int radk_ctx_peer_handle(radk_ctx *c, void *handle) {
+	if (c && c->split_mode) { set_error("radk_ctx_peer_handle: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !handle) { set_error("radk_ctx_peer_handle: null argument"); return RADK_ERR_ARG; }
 	if (!c->use_fast) { set_error("radk_ctx_peer_handle: context does not use the batched path"); return RADK_ERR_STATE; }
 	static_assert(sizeof(cudaIpcMemHandle_t) == RADK_PEER_HANDLE_BYTES, "handle size");
@@ -809,6 +1026,7 @@ int radk_ctx_peer_connect_local(radk_ctx *c, radk_ctx *const *peers, int world) 
 }
 
 int radk_ctx_owned_slots(radk_ctx *c, int *slots, int cap, int *n) {
+	if (c && c->split_mode) { set_error("radk_ctx_owned_slots: not available on adaptive-split contexts"); return RADK_ERR_STATE; }
 	if (!c || !n) { set_error("radk_ctx_owned_slots: null argument"); return RADK_ERR_ARG; }
 	*n = c->R;
 	if (slots)

@@ -33,6 +33,17 @@ VARIANTS = {  # extra option sets: name -> (model, reference argv, shots)
 }
 
 
+# split-enabled reference ("variant A", oracle/ref_harness/variantA/config.h), single thread (the
+# reference races otherwise).  *_nosample: -sample_area so large that no rand() sample is drawn, which
+# makes the split decisions deterministic and exactly reproducible on the GPU.
+SPLIT_VARIANTS = {
+    "blocks_split": ("blocks", ["-adapt_area", "5"]),
+    "blocks_split_nosample": ("blocks", ["-adapt_area", "5", "-sample_area", "1000000000"]),
+    "sbox_split_nosample": ("sbox", ["-adapt_area", "2", "-sample_area", "1000000000"]),
+    "room_split_nosample": ("room", ["-adapt_area", "20", "-sample_area", "1000000000", "-triangle", "60000"]),
+}
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -44,10 +55,10 @@ def state_digest(sc):
             "accB_sum": float(sc.slots["accB"][live].astype(np.float64).sum())}
 
 
-def run_harness(tri, extra, shots, tmp, tag, write_fin=False):
-    harness = po.ref_binary("ref_harness")
+def run_harness(tri, extra, shots, tmp, tag, write_fin=False, binary="ref_harness", jobs=None):
+    harness = po.ref_binary(binary)
     assert harness, "build oracle/_ref first (make -C oracle)"
-    args = [harness, "-jobs", str(os.cpu_count()), "-o", os.path.join(tmp, tag), tri] + extra + [
+    args = [harness, "-jobs", str(jobs or os.cpu_count()), "-o", os.path.join(tmp, tag), tri] + extra + [
         "--dump-scene", os.path.join(tmp, tag + ".scene"), "--dump-final", os.path.join(tmp, tag + ".final"),
         "--dump-shooters", os.path.join(tmp, tag + ".shooters"), "--json"]
     if shots >= 0:
@@ -99,6 +110,16 @@ def main():
             res.update({"model": model, "argv": extra, "tristore_sha": sha(sc.slots), "scene_trinum": info["trinum"]})
             gold["variants"][vname] = res
             print(vname, info["trinum"], res["shots"], flush=True)
+        gold["split_variants"] = {}
+        for vname, (model, extra) in SPLIT_VARIANTS.items():
+            tri = os.path.join(tmp, model + ".tri")
+            info, res = run_harness(tri, extra, -1, tmp, vname, binary="ref_harness_split", jobs=1)
+            fin = po.Scene.from_dump(os.path.join(tmp, vname + ".final"))
+            live = fin.slots["parent"] >= 0
+            res.update({"model": model, "argv": extra, "parent_sha": sha(fin.slots["parent"]), "p_sha": sha(fin.slots["p"][live]),
+                        "deltaB_sum": float(fin.slots["deltaB"][live].astype(np.float64).sum())})
+            gold["split_variants"][vname] = res
+            print(vname, res["trinum"], res["leaves"], res["shots"], flush=True)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
         f.write("\n")
