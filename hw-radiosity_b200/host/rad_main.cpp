@@ -9,6 +9,8 @@
 //   -gpu <n>        CUDA device ordinal (default 0)
 //   -max_tri <n>    raise the reference's compile-time MaxTri pool limit (rad.h:9)
 //   -stats          print device ray statistics at the end
+//   -split          adaptive splitting inside the loop on the device (the reference's split-enabled build:
+//                   config.h without DONT_PARTITION/PRE_PARTITION); -adapt_area/-sample_area/-delta_ff then act
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -31,7 +33,7 @@ struct Options {
 	int triangle = 1000000;
 	float light = 1.0f;
 	int write_cycle = 10, zip = 0, interactive = 0, jobs = 2, parallel_src = 1;
-	int gpu = 0, max_tri = 0, stats = 0;
+	int gpu = 0, max_tri = 0, stats = 0, split = 0;
 	const char *input = nullptr;
 	const char *prefix = "./test";
 };
@@ -77,6 +79,7 @@ void usage(const char *argv0, const Options &d) {
 	fprintf(stderr, "                               " KMAG "Defulat false\n" KWHT);
 	fprintf(stderr, "   Device Options (this implementation)\n");
 	fprintf(stderr, "       -gpu <integer>          CUDA device ordinal.  -max_tri <integer>  triangle pool size.  -stats\n");
+	fprintf(stderr, "       -split                  Adaptive splitting inside the loop (reference built without DONT_PARTITION).\n");
 }
 
 bool want_int(int argc, char **argv, int &i, int &dst, const char *what) {
@@ -119,6 +122,7 @@ bool process_options(int argc, char **argv, Options &o) {
 		else if (a == "-gpu") ok = want_int(argc, argv, i, o.gpu, "GPU");
 		else if (a == "-max_tri") ok = want_int(argc, argv, i, o.max_tri, "MaxTri");
 		else if (a == "-stats") o.stats = 1;
+		else if (a == "-split") o.split = 1;
 		else o.input = argv[i];		// rad.cpp:625-626: anything unrecognised is the input file
 		if (!ok) return false;
 	}
@@ -143,6 +147,18 @@ void after_write(const Options &o, const std::string &fn) {
 }
 
 bool write_snapshot(radk_ctx *ctx, radk_model *model, const Options &o, int loop) {
+	if (o.split) {		// the pool grew on the device: fetch whole records
+		int n = 0;
+		radk_ctx_download_triangles(ctx, nullptr, 0, &n);
+		std::vector<radk_triangle> all((size_t)n);
+		if (radk_ctx_download_triangles(ctx, all.data(), n, &n) != RADK_OK || radk_model_set_triangles(model, all.data(), n) != RADK_OK) {
+			fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
+			return false;
+		}
+		if (radk_model_write(model, o.prefix, loop) != RADK_OK) return loop != 0;
+		after_write(o, std::string(o.prefix) + (loop == 0 ? std::string(".fin") : "." + std::to_string(loop)));
+		return true;
+	}
 	int trinum = 0;
 	radk_triangle *tri = radk_model_triangles(model, &trinum);
 	std::vector<float> acc((size_t)trinum * 9), dB((size_t)trinum * 3);
@@ -176,6 +192,7 @@ int main(int argc, char **argv) {
 	radk_model_opts mo;
 	radk_default_model_opts(&mo);
 	mo.light_scale = o.light, mo.tri_limit = o.triangle, mo.sample_area = o.sample_area;
+	if (o.split) mo.prepartition = 0;	// the split-enabled reference build has no PrePartition pass
 	if (o.max_tri > 0) mo.max_tri = o.max_tri;
 	radk_model *model = nullptr;
 	double t0 = now();
@@ -209,14 +226,16 @@ int main(int argc, char **argv) {
 	printf("       -parallel_src   %d\n", o.parallel_src);
 	printf("[" KGRN "INFO" KWHT "] Complete initialization\n");
 	fflush(stdout);
-	fprintf(stderr, "[" KRED "DEBUG" KWHT "] Before PrePartitionTriangle %d\n", sc.n0);
-	fprintf(stderr, "[" KRED "DEBUG" KWHT "] After PrePartitionTriangle %d\n", sc.trinum);
+	if (!o.split) {
+		fprintf(stderr, "[" KRED "DEBUG" KWHT "] Before PrePartitionTriangle %d\n", sc.n0);
+		fprintf(stderr, "[" KRED "DEBUG" KWHT "] After PrePartitionTriangle %d\n", sc.trinum);
+	}
 
 	radk_opts co;
 	radk_default_opts(&co);
 	co.converge = o.converge, co.parallel_src = o.parallel_src, co.tri_limit = o.triangle;
 	co.area_limit = o.adapt_area, co.sample_area = radk_model_sample_area(model), co.delta_ff = o.delta_ff;
-	co.device = o.gpu, co.collect_stats = o.stats;
+	co.device = o.gpu, co.collect_stats = o.stats, co.split_enabled = o.split;
 	if (o.max_tri > 0) co.max_tri = o.max_tri;
 	radk_ctx *ctx = nullptr;
 	if (radk_ctx_create(&sc, &co, &ctx) != RADK_OK) {

@@ -61,3 +61,14 @@ def test_zip_option(models_dir, tmp_path):
     r = run(RAD, ["-zip", str(models_dir / "model2s.tri"), "-o", "z"], tmp_path)
     assert r.returncode == 0
     assert os.path.exists(tmp_path / "z.fin.gz") and b"Compress output file z.fin ." in r.stdout
+
+
+@pytest.mark.gpu
+def test_split_switch_matches_split_enabled_reference(models_dir, golden, tmp_path):
+    """`rad -split` = the reference compiled without DONT_PARTITION/PRE_PARTITION; exact when no random sample is drawn."""
+    g = golden["split_variants"]["blocks_split_nosample"]
+    r = run(RAD, ["-split"] + g["argv"] + [str(models_dir / "blocks.tri"), "-o", "s"], tmp_path)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")
+    assert re.findall(rb"Complete in #Iterations (\d+)", r.stderr) == [str(g["shots"] + 1).encode()]
+    text = (tmp_path / "s.fin").read_bytes()
+    assert text.count(b"Triangle \n") == g["leaves"]
