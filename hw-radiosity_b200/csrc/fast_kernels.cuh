@@ -623,7 +623,14 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			// shot (thread b polls CTA b's), which is the grid barrier and the payload fetch in one round trip
 			const unsigned tag = F.launch_tag | epoch;
 			TaggedPartial *slots = F.tpartial + (size_t)parity * max_ctas;
-			if (threadIdx.x == 0) store_tagged(&slots[blockIdx.x], s_best.key, s_best.dB[0], s_best.dB[1], s_best.dB[2], tag);
+			// arrival is signalled through one counter (a single poller per CTA keeps L2 quiet); the counter is bumped
+			// without a fence - if it overtakes a record, the record's tag does not match yet and the load is retried
+			if (threadIdx.x == 0) {
+				store_tagged(&slots[blockIdx.x], s_best.key, s_best.dB[0], s_best.dB[1], s_best.dB[2], tag);
+				atomicAdd(F.barrier, 1u);
+				while (*((volatile unsigned *)F.barrier) < epoch * (unsigned)nctas) { }
+			}
+			__syncthreads();
 			unsigned long long k = 0ull;
 			float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 			if (threadIdx.x < nctas) {
