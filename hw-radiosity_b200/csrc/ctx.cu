@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <unordered_map>
@@ -89,8 +90,6 @@ struct radk_ctx {
 	DevBuf<unsigned> fast_uints;			// [0]=ticket [1]=barrier
 	DevBuf<ShotRec> handoff;
 	DevBuf<Partial> partial;
-	DevBuf<TaggedPartial> tpartial;
-	unsigned launch_seq = 0;
 	DevBuf<long long> budget;
 	DevBuf<PeerBox> box;
 	DevBuf<unsigned long long> pred_round;
@@ -156,9 +155,6 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	ff_batch_kernel<<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	int max_ctas = c->shots_ctas;
-	c->launch_seq = (c->launch_seq % 4095u) + 1u;	// tags of consecutive launches never coincide (epoch < 2^20 per launch)
-	if (c->launch_seq == 1u) CUDA_TRY(cudaMemsetAsync(c->tpartial.p, 0, 2 * (size_t)c->shots_ctas * sizeof(TaggedPartial), st));	// tag space wrapped
-	c->F.launch_tag = c->launch_seq << 20;
 	void *args[] = {(void *)&c->S, (void *)&c->F, (void *)&max_ctas};
 	CUDA_TRY(cudaLaunchCooperativeKernel(c->shots_fn, dim3((unsigned)c->shots_ctas), dim3(kShotsBlock), args, 0, st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
@@ -402,8 +398,6 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		CUDA_TRY(c->fast_uints.alloc(4));
 		CUDA_TRY(c->handoff.alloc(1));
 		CUDA_TRY(c->partial.alloc(2 * (size_t)c->shots_ctas));
-		CUDA_TRY(c->tpartial.alloc(2 * (size_t)c->shots_ctas));
-		CUDA_TRY(cudaMemsetAsync(c->tpartial.p, 0, 2 * (size_t)c->shots_ctas * sizeof(TaggedPartial), st));
 		CUDA_TRY(c->budget.alloc(1));
 		CUDA_TRY(c->box.alloc(1));
 		CUDA_TRY(c->pred_round.alloc(1));
@@ -415,8 +409,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.ff = c->ffcache.p, F.rows = rows, F.row_slot = c->row_slot.p, F.slot_row = c->slot_row.p;
 		F.rec = c->row_rec.p, F.todo = c->todo.p, F.ntodo = c->fast_ints.p, F.stalled = c->fast_ints.p + 1;
 		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.barrier = c->fast_uints.p + 1;
-		F.handoff = c->handoff.p, F.partial = c->partial.p, F.tpartial = c->tpartial.p, F.budget = c->budget.p;
-		F.launch_tag = 0;
+		F.handoff = c->handoff.p, F.partial = c->partial.p, F.budget = c->budget.p;
 		F.row_mask = c->row_mask.p, F.mask_words = mask_words;
 		for (int t = 0; t < kMaxWorld; t++) F.box[t] = nullptr;
 		F.box[o.rank] = c->box.p;

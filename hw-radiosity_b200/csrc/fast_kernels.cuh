@@ -35,36 +35,11 @@ struct ShotRec {		// the shooter of the next shot, handed from shot to shot / ke
 	int pad[2];
 };
 
-struct Partial {		// one CTA's best candidate of a shot
+struct alignas(32) Partial {	// one CTA's best candidate of a shot
 	unsigned long long key;
 	float dB[3];
 	int pad;
 };
-
-// Tagged form used between the CTAs of one GPU: two 16-byte halves, each carrying the shot tag, written
-// with one 128-bit store per half and polled with one 128-bit load per half.  A half is consistent in
-// itself (aligned 16-byte accesses are single transactions), and the record is complete once both
-// halves show the expected tag - so the record doubles as its own arrival flag: no counter, no fence,
-// no second round trip to fetch the payload.
-struct alignas(32) TaggedPartial {
-	uint4 h0;	// key lo, key hi, dB0 bits, tag
-	uint4 h1;	// dB1 bits, dB2 bits, tag, 0
-};
-__device__ __forceinline__ void store_tagged(TaggedPartial *dst, unsigned long long key, float d0, float d1, float d2, unsigned tag) {
-	const uint4 a = make_uint4((unsigned)key, (unsigned)(key >> 32), __float_as_uint(d0), tag);
-	const uint4 b = make_uint4(__float_as_uint(d1), __float_as_uint(d2), tag, 0u);
-	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&dst->h0), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
-	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&dst->h1), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-}
-__device__ __forceinline__ bool load_tagged(const TaggedPartial *src, unsigned tag, unsigned long long *key, float *d0, float *d1, float *d2) {
-	uint4 a, b;
-	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(&src->h0) : "memory");
-	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(&src->h1) : "memory");
-	if (a.w != tag || b.z != tag) return false;
-	*key = ((unsigned long long)a.y << 32) | a.x;
-	*d0 = __uint_as_float(a.z), *d1 = __uint_as_float(b.x), *d2 = __uint_as_float(b.y);
-	return true;
-}
 
 // ---- multi-GPU mailboxes (one PeerBox per rank, in that rank's HBM, mapped into every peer) ---------
 // Ranks exchange (a) per round: their local top candidates with full shooter records, (b) per shot:
@@ -101,9 +76,7 @@ struct FastState {
 	unsigned long long *group_key;	// [kPredictGroups]
 	unsigned *ticket;
 	ShotRec *handoff;		// current shooter between kernels
-	Partial *partial;		// [2][max CTAs] (multi-GPU path: counter barrier + plain records)
-	TaggedPartial *tpartial;	// [2][max CTAs] (single-GPU path: self-flagging records)
-	unsigned launch_tag;		// distinguishes the tags of different shots_kernel launches (bits 20..31)
+	Partial *partial;		// [2][max CTAs], 32-byte records
 	unsigned *barrier;		// grid barrier counter (zeroed before each shots launch)
 	long long *budget;		// shots the current radk_ctx_step call may still run
 	unsigned *row_mask;		// [rows][mask_words] bit n set <=> leaf n's list contains the row's logsrc
@@ -495,7 +468,7 @@ constexpr int kShotsBlock = 512;
 // CalRadiosity (shade.cpp:244-259) of one receiver from cached vertex form factors.
 __device__ __forceinline__ void apply_shot(float4 &a0, float4 &a1, float4 &a2, const int4 &id, const float4 &fk,
 					   const float2 *__restrict__ ffrow, float sdB0, float sdB1, float sdB2) {
-	const float2 h0 = ffrow[id.x], h1 = ffrow[id.y], h2 = ffrow[id.z];	// L1-cacheable: rows are read-only during this kernel
+	const float2 h0 = __ldcg(&ffrow[id.x]), h1 = __ldcg(&ffrow[id.y]), h2 = __ldcg(&ffrow[id.z]);
 	const float ff[3] = {h0.x + h0.y, h1.x + h1.y, h2.x + h2.y};
 	const float lo[3] = {fk.x * sdB0 / 3, fk.y * sdB1 / 3, fk.z * sdB2 / 3};	// shade.cpp:247-249
 	float dB[3] = {a0.w, a1.w, a2.w};
@@ -523,7 +496,6 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 	__shared__ unsigned long long s_key[kShotsBlock / 32];
 	__shared__ float s_dB[kShotsBlock / 32][3];
 	__shared__ Partial s_best;
-	__shared__ unsigned long long s_key2[kShotsBlock / 32];	// runner-up (prefetch hint only)
 	__shared__ int s_row_slot[kMaxRows];			// cache directory: slot held by each row
 	__shared__ int s_next_row;
 	constexpr int NR = RPT > 0 ? RPT : 1;
@@ -563,7 +535,7 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 	long long done = 0;
 	int stalled = 0;
 	while (true) {
-		if (!cur.valid || budget <= 0 || epoch >= 1000000u) break;	// (tags carry 20 bits of shot number per launch)
+		if (!cur.valid || budget <= 0) break;
 		if (cur.row < 0) { stalled = 1; break; }
 		const float2 *ffrow = F.ff + (size_t)cur.row * S.U;
 		const int shooter_slot = cur.slot;
@@ -619,57 +591,32 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 		__syncthreads();	// s_key / s_dB are reused below
 		epoch++;
 		if (F.world == 1) {
-			// single GPU: the CTA's best goes out as a self-flagging record; every CTA polls all records of this
-			// shot (thread b polls CTA b's), which is the grid barrier and the payload fetch in one round trip
-			const unsigned tag = F.launch_tag | epoch;
-			TaggedPartial *slots = F.tpartial + (size_t)parity * max_ctas;
-			// arrival is signalled through one counter (a single poller per CTA keeps L2 quiet); the counter is bumped
-			// without a fence - if it overtakes a record, the record's tag does not match yet and the load is retried
-			if (threadIdx.x == 0) {
-				store_tagged(&slots[blockIdx.x], s_best.key, s_best.dB[0], s_best.dB[1], s_best.dB[2], tag);
-				atomicAdd(F.barrier, 1u);
-				while (*((volatile unsigned *)F.barrier) < epoch * (unsigned)nctas) { }
-			}
-			__syncthreads();
+			// single GPU: publish the CTA's best, one grid barrier, then every CTA reduces all records the same way
+			// (identical `cur` everywhere, no second barrier).  The whole 32-byte record comes with one pair of
+			// 128-bit loads, and the winner's cache row is looked up in the shared-memory directory, so the
+			// barrier is followed by a single L2 round trip.
+			if (threadIdx.x == 0) F.partial[parity * max_ctas + blockIdx.x] = s_best;
+			grid_barrier(F.barrier, epoch * (unsigned)nctas);
 			unsigned long long k = 0ull;
 			float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 			if (threadIdx.x < nctas) {
-				while (!load_tagged(&slots[threadIdx.x], tag, &k, &d0, &d1, &d2)) { }
+				const uint4 *rec = (const uint4 *)&F.partial[parity * max_ctas + threadIdx.x];
+				const uint4 a = __ldcg(rec), bb = __ldcg(rec + 1);
+				k = ((unsigned long long)a.y << 32) | a.x;
+				d0 = __uint_as_float(a.z), d1 = __uint_as_float(a.w), d2 = __uint_as_float(bb.x);
 			}
-			// CTA-wide max with the winner's payload, plus the runner-up key as a prefetch hint
 			const unsigned long long m1 = warp_max_u64(k);
-			const unsigned long long k2 = (k == m1) ? 0ull : k;
-			const unsigned long long r1 = warp_max_u64(k2);
-			if (lane == 0) s_key[warp] = m1, s_key2[warp] = r1;
+			if (lane == 0) s_key[warp] = m1;
 			__syncthreads();
-			unsigned long long m = 0ull, m2 = 0ull;
-			for (int w = 0; w < kShotsBlock / 32; w++) {
-				const unsigned long long a = s_key[w], b = s_key2[w];
-				if (a > m) m2 = m > b ? m : b, m = a;
-				else m2 = (a > m2 ? a : m2) > b ? (a > m2 ? a : m2) : b;
-			}
+			unsigned long long m = 0ull;
+			for (int w = 0; w < kShotsBlock / 32; w++) m = s_key[w] > m ? s_key[w] : m;
 			if (m != 0ull && k == m) s_best.key = m, s_best.dB[0] = d0, s_best.dB[1] = d1, s_best.dB[2] = d2;
 			if (threadIdx.x == 0 && m == 0ull) s_best.key = 0ull;
-			// cache directory lookups from shared memory (warp 0): rows of the winner and of the runner-up
-			if (warp == 0) {
-				const int mine = s_row_slot[lane];
-				const unsigned hit1 = __ballot_sync(0xffffffffu, m != 0ull && mine == (int)(m & 0xffffffffu));
-				const unsigned hit2 = __ballot_sync(0xffffffffu, m2 != 0ull && mine == (int)(m2 & 0xffffffffu));
-				if (lane == 0) s_next_row = hit1 ? __ffs(hit1) - 1 : -1, s_key2[0] = hit2 ? (unsigned long long)(__ffs(hit2) - 1) : ~0ull;
+			if (warp == 0) {	// cache directory lookup from shared memory
+				const unsigned hit = __ballot_sync(0xffffffffu, m != 0ull && s_row_slot[lane] == (int)(m & 0xffffffffu));
+				if (lane == 0) s_next_row = hit ? __ffs(hit) - 1 : -1;
 			}
 			__syncthreads();
-			if (RPT > 0 && s_key2[0] != ~0ull) {
-				// the runner-up is the likely shooter after the next one: pull its form factors of this thread's
-				// receivers into L1 now, so that shot's gathers do not wait for L2
-				const float2 *pf = F.ff + (size_t)s_key2[0] * S.U;
-#pragma unroll
-				for (int q = 0; q < NR; q++)
-					if (rslot[q] >= 0) {
-						asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + rid[q].x));
-						asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + rid[q].y));
-						asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + rid[q].z));
-					}
-			}
 		} else {
 			// multi-GPU: CTA 0 waits for the local CTAs, reduces their partials and mails the rank's best to every
 			// rank; every CTA (on every rank) then waits for all ranks' mail in its own box.
