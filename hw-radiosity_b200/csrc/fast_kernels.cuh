@@ -608,8 +608,7 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			const unsigned long long m1 = warp_max_u64(k);
 			if (lane == 0) s_key[warp] = m1;
 			__syncthreads();
-			unsigned long long m = 0ull;
-			for (int w = 0; w < kShotsBlock / 32; w++) m = s_key[w] > m ? s_key[w] : m;
+			const unsigned long long m = warp_max_u64(lane < kShotsBlock / 32 ? s_key[lane] : 0ull);	// every warp reduces the warp maxima
 			if (m != 0ull && k == m) s_best.key = m, s_best.dB[0] = d0, s_best.dB[1] = d1, s_best.dB[2] = d2;
 			if (threadIdx.x == 0 && m == 0ull) s_best.key = 0ull;
 			if (warp == 0) {	// cache directory lookup from shared memory
