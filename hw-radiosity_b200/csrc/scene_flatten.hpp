@@ -1,8 +1,8 @@
 // Host-side flattening of a scene into the arrays the kernels read (pure C++, no CUDA calls):
 //  * the octree becomes a dense cell->leaf table + per-node float4 records + the leaf lists,
 //  * occluders TriStore[0..n0) become 5 float4 each,
-//  * receivers (slots with parent >= 0) are sorted by (original parent, Morton code), sharded by
-//    rank, and split into float4 planes; vertices shared by receivers of one original are merged.
+//  * receivers (slots with parent >= 0) are sorted by (original parent, Morton code), dealt to the ranks
+//    in blocks of 512, and split into float4 planes; vertices shared by receivers of one original are merged.
 #pragma once
 #include <algorithm>
 #include <cstring>
@@ -184,9 +184,14 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 	std::sort(order.begin(), order.end(), [&](int a, int b) { return lkey[a] != lkey[b] ? lkey[a] < lkey[b] : leaves[a] < leaves[b]; });
 	F.leaves_total = (int)leaves.size();
 	if (world < 1) world = 1;
-	const long long L = (long long)leaves.size();
-	const int lo_i = (int)(L * rank / world), hi_i = (int)(L * (rank + 1) / world);
-	const int R = hi_i - lo_i;
+	// block-cyclic sharding of the sorted receivers: blocks of kShardBlock neighbours are dealt round-robin, so
+	// every rank gets an even sample of the scene (contiguous halves differ a lot in how far their rays travel)
+	constexpr int kShardBlock = 512;
+	std::vector<int> mine;
+	mine.reserve(leaves.size() / world + kShardBlock);
+	for (size_t i = 0; i < leaves.size(); i++)
+		if ((int)((i / kShardBlock) % (size_t)world) == rank) mine.push_back((int)i);
+	const int R = (int)mine.size();
 	F.R = R;
 	F.recv_slot.resize(R);
 	F.recv_parent.resize(R);
@@ -211,7 +216,7 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 		}
 	}
 	for (int r = 0; r < R; r++) {
-		const int slot = leaves[order[lo_i + r]];
+		const int slot = leaves[order[mine[r]]];
 		const radk_triangle &t = s->tri[slot];
 		F.recv_slot[r] = slot;
 		F.recv_parent[r] = t.parent;

@@ -82,7 +82,7 @@ typedef struct radk_opts {
 	int max_tri;		/* the reference's MaxTri (rad.h:9); 0 = 1000000 */
 	int split_enabled;	/* 0 = shipped configuration (DONT_PARTITION); 1 = adaptive centre split */
 	int device;		/* CUDA device ordinal */
-	int rank, world;	/* receiver shard: this context owns leaves [rank*L/world, (rank+1)*L/world) */
+	int rank, world;	/* receiver shard: the sorted receivers are dealt to the ranks in blocks of 512 */
 	int collect_stats;	/* 1: count rays / visits / tests on the device (slower kernels) */
 	int dedup;		/* 1 (default when 0 is not forced by split_enabled): evaluate each unique
 				 * (vertex, parent) once per shot; -1: force per-receiver evaluation */
