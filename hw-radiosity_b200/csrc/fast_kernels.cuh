@@ -53,9 +53,31 @@ struct PredCand {
 	ShooterRec rec;
 	int pad[2];
 };
+// Per-shot mail is self-validating: two 16-byte halves, each carrying the shot tag and written with one
+// 128-bit store, so no system-scope fence and no separate flag are needed (a half is one NVLink write).
+struct alignas(32) ShotMail {
+	uint4 h0;	// key lo, key hi, dB0 bits, tag
+	uint4 h1;	// dB1 bits, dB2 bits, tag, 0
+};
+__device__ __forceinline__ void send_mail(ShotMail *dst, const Partial &p, unsigned tag) {
+	const unsigned long long key = p.key;
+	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&dst->h0), "r"((unsigned)key), "r"((unsigned)(key >> 32)),
+		     "r"(__float_as_uint(p.dB[0])), "r"(tag) : "memory");
+	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&dst->h1), "r"(__float_as_uint(p.dB[1])),
+		     "r"(__float_as_uint(p.dB[2])), "r"(tag), "r"(0u) : "memory");
+}
+__device__ __forceinline__ bool read_mail(const ShotMail *src, unsigned tag, Partial *out) {
+	uint4 a, b;
+	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(&src->h0) : "memory");
+	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(&src->h1) : "memory");
+	if (a.w != tag || b.z != tag) return false;
+	out->key = ((unsigned long long)a.y << 32) | a.x;
+	out->dB[0] = __uint_as_float(a.z), out->dB[1] = __uint_as_float(b.x), out->dB[2] = __uint_as_float(b.y), out->pad = 0;
+	return true;
+}
+
 struct PeerBox {
-	Partial shot[2][kMaxWorld];
-	unsigned long long shot_seq[2][kMaxWorld];
+	ShotMail shot[2][kMaxWorld];
 	PredCand pred[2][kMaxWorld][kMaxRows];
 	unsigned long long pred_seq[2][kMaxWorld];
 };
@@ -619,7 +641,7 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 		} else {
 			// multi-GPU: CTA 0 waits for the local CTAs, reduces their partials and mails the rank's best to every
 			// rank; every CTA (on every rank) then waits for all ranks' mail in its own box.
-			const unsigned long long seq = (F.epoch << 40) | (unsigned long long)(shots_before + done + 1);
+			const unsigned tag = (unsigned)F.epoch * 0x9E3779B1u + (unsigned)(shots_before + done + 1);	// never equals a stale slot's tag
 			__syncthreads();
 			if (threadIdx.x == 0) { __threadfence(); atomicAdd(F.barrier, 1u); }
 			if (blockIdx.x == 0) {
@@ -646,28 +668,27 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 					s_best.key = m, s_best.dB[0] = __ldcg(&p->dB[0]), s_best.dB[1] = __ldcg(&p->dB[1]), s_best.dB[2] = __ldcg(&p->dB[2]);
 				}
 				__syncthreads();
-				if (threadIdx.x < F.world) {
-					PeerBox *dst = F.box[threadIdx.x];
-					peer_copy(&dst->shot[parity][F.rank], &s_best, (int)sizeof(Partial));
-					__threadfence_system();
-					*((volatile unsigned long long *)&dst->shot_seq[parity][F.rank]) = seq;
-				}
+				if (threadIdx.x < F.world) send_mail(&F.box[threadIdx.x]->shot[parity][F.rank], s_best, tag);
 			}
 			__shared__ int s_ok;
 			if (threadIdx.x == 0) s_ok = 1;
 			__syncthreads();
 			PeerBox *mine = F.box[F.rank];
-			if (threadIdx.x < F.world && !peer_wait(&mine->shot_seq[parity][threadIdx.x], seq)) s_ok = 0;
+			__shared__ Partial s_mail[kMaxWorld];
+			if (threadIdx.x < F.world) {
+				const long long t0 = clock64();
+				unsigned spins = 0;
+				while (!read_mail(&mine->shot[parity][threadIdx.x], tag, &s_mail[threadIdx.x])) {
+					if ((++spins & 0xfff) == 0 && clock64() - t0 > 40000000000ll) { s_ok = 0; break; }
+				}
+			}
 			__syncthreads();
 			if (threadIdx.x == 0) {
 				Partial best;
 				best.key = 0ull, best.dB[0] = best.dB[1] = best.dB[2] = 0.0f, best.pad = 0;
 				if (s_ok) {
-					for (int t = 0; t < F.world; t++) {
-						const volatile Partial *p = &mine->shot[parity][t];
-						const unsigned long long kk = p->key;
-						if (kk > best.key) best.key = kk, best.dB[0] = p->dB[0], best.dB[1] = p->dB[1], best.dB[2] = p->dB[2];
-					}
+					for (int t = 0; t < F.world; t++)
+						if (s_mail[t].key > best.key) best = s_mail[t];
 				} else {
 					*F.error = 1;
 				}
