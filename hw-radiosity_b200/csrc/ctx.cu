@@ -94,6 +94,7 @@ struct radk_ctx {
 	DevBuf<PeerBox> box;
 	DevBuf<unsigned long long> pred_round;
 	DevBuf<int> fast_error;
+	DevBuf<unsigned long long> dbg;
 	std::vector<void *> ipc_opened;
 	bool peers_connected = false;
 	unsigned long long epoch = 0;
@@ -415,6 +416,8 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.box[o.rank] = c->box.p;
 		F.rank = o.rank, F.world = world;
 		F.pred_round = c->pred_round.p, F.error = c->fast_error.p;
+		F.dbg = nullptr;
+		if (getenv("RADK_DEBUG_PREDICT")) { CUDA_TRY(c->dbg.alloc(16)); CUDA_TRY(cudaMemsetAsync(c->dbg.p, 0, 16 * 8, st)); F.dbg = c->dbg.p; }
 		c->peers_connected = world == 1;
 		int rc2 = reset_fast_state(c);
 		if (rc2) return rc2;
@@ -547,6 +550,12 @@ void radk_ctx_destroy(radk_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->dbg.p) {	// RADK_DEBUG_PREDICT: phases of the last predict_kernel launch
+		unsigned long long t[16];
+		if (cudaMemcpy(t, c->dbg.p, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
+			fprintf(stderr, "[radk] predict phases (ns): scan+ticket %llu, top-K %llu, cache rebuild %llu, shooter records %llu, leaf masks %llu\n",
+				t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
+	}
 	if (c->h_flags) cudaFreeHost(c->h_flags);
 	if (c->h_shots) cudaFreeHost(c->h_shots);
 	if (c->h_budget) cudaFreeHost(c->h_budget);

@@ -88,6 +88,7 @@ struct FastState {
 	unsigned long long epoch;	// run epoch (bumped by reset / rewind on every rank alike)
 	unsigned long long *pred_round;	// rounds predicted so far in this epoch (device)
 	int *error;			// set when a peer wait timed out
+	unsigned long long *dbg;	// optional [16] %globaltimer stamps of predict_kernel's phases (nullptr = off)
 	float2 *ff;			// [rows][U] cached form factors: .x toward half 0, .y toward half 1
 	int rows;			// cache capacity (<= kMaxRows)
 	int *row_slot;			// [rows] slot whose form factors the row holds, -1 free
@@ -158,19 +159,18 @@ __device__ int rebuild_cache(const FastState &F, const unsigned long long *top, 
 	return nt;
 }
 
-// Leaf masks of the new rows (all threads of the CTA): which leaves list the shooter's original triangle.
+// Leaf masks of the new rows: which leaves list the shooter's original triangle.  One warp per row, all rows
+// in flight together (the chain todo -> record -> inverted index -> leaves is four dependent loads).
 __device__ void build_row_masks(const DevScene &S, const FastState &F, int nt) {
-	for (int t = 0; t < nt; t++) {
-		unsigned *mask = F.row_mask + (size_t)F.todo[t] * F.mask_words;
-		for (int w = threadIdx.x; w < F.mask_words; w += blockDim.x) mask[w] = 0u;
-	}
-	__syncthreads();
-	for (int t = 0; t < nt; t++) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	for (int t = warp; t < nt; t += nwarps) {
 		const int row = F.todo[t];
-		const int logsrc = F.rec[row].logsrc;
 		unsigned *mask = F.row_mask + (size_t)row * F.mask_words;
+		for (int w = lane; w < F.mask_words; w += 32) mask[w] = 0u;
+		__syncwarp();
+		const int logsrc = F.rec[row].logsrc;
 		const int b = S.tree.tri_leaf_begin[logsrc], e = S.tree.tri_leaf_begin[logsrc + 1];
-		for (int k = b + threadIdx.x; k < e; k += blockDim.x) {
+		for (int k = b + lane; k < e; k += 32) {
 			const int leaf = S.tree.tri_leaves[k];
 			atomicOr(&mask[leaf >> 5], 1u << (leaf & 31));
 		}
@@ -178,9 +178,18 @@ __device__ void build_row_masks(const DevScene &S, const FastState &F, int nt) {
 }
 
 // ---- predict ------------------------------------------------------------------------------------
+__device__ __forceinline__ void dbg_stamp(const FastState &F, int i) {
+	if (F.dbg && threadIdx.x == 0) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		F.dbg[i] = t;
+	}
+}
+
 __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
 	__shared__ bool s_last;
 	__shared__ int s_ntodo;
+	if (blockIdx.x == 0) dbg_stamp(F, 0);
 	const int T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	// thread t only sees receivers r == t (mod T); T is a multiple of kPredictGroups, so its running
 	// maximum belongs to group t % kPredictGroups
@@ -197,26 +206,43 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence();
-	// ---- last CTA: the `rows` largest group maxima, by repeated CTA-wide argmax (each thread owns two keys)
-	__shared__ unsigned long long wmax[2][32];
+	dbg_stamp(F, 1);
+	// ---- last CTA: the `rows` largest group maxima.  Threads 0..255 own eight keys each; per round a thread
+	// maximum, an 8-warp reduction and one named barrier of 256 threads - the other 24 warps wait below.
+	__shared__ unsigned long long wmax[2][8];
 	__shared__ unsigned long long top[kMaxRows];
-	unsigned long long k0 = __ldcg(&F.group_key[threadIdx.x]), k1 = __ldcg(&F.group_key[threadIdx.x + 1024]);
-	F.group_key[threadIdx.x] = 0ull, F.group_key[threadIdx.x + 1024] = 0ull;	// ready for the next round
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int rows = F.rows;
-	for (int it = 0; it < rows; it++) {
-		const unsigned long long mine = k0 > k1 ? k0 : k1;
-		const unsigned long long wm = warp_max_u64(mine);
-		if (lane == 0) wmax[it & 1][warp] = wm;
-		__syncthreads();
-		const unsigned long long m = warp_max_u64(wmax[it & 1][lane]);	// every warp reduces the 32 warp maxima
-		if (m != 0ull) {
-			if (k0 == m) k0 = 0ull;
-			if (k1 == m) k1 = 0ull;
+	if (threadIdx.x < kMaxRows) top[threadIdx.x] = 0ull;
+	__syncthreads();
+	if (threadIdx.x < 256) {
+		unsigned long long k[kPredictGroups / 256];
+#pragma unroll
+		for (int q = 0; q < kPredictGroups / 256; q++) {
+			k[q] = __ldcg(&F.group_key[threadIdx.x + 256 * q]);
+			F.group_key[threadIdx.x + 256 * q] = 0ull;	// ready for the next round
 		}
-		if (threadIdx.x == 0) top[it] = m;
+		for (int it = 0; it < rows; it++) {
+			unsigned long long mine = 0ull;
+#pragma unroll
+			for (int q = 0; q < kPredictGroups / 256; q++) mine = k[q] > mine ? k[q] : mine;
+			const unsigned long long wm = warp_max_u64(mine);
+			if (lane == 0) wmax[it & 1][warp] = wm;
+			asm volatile("bar.sync 1, 256;" ::: "memory");
+			unsigned long long m = 0ull;
+#pragma unroll
+			for (int w = 0; w < 8; w++) m = wmax[it & 1][w] > m ? wmax[it & 1][w] : m;
+			if (m == 0ull) break;		// fewer candidates than rows (uniform across the 256 threads)
+			if (mine == m) {
+#pragma unroll
+				for (int q = 0; q < kPredictGroups / 256; q++)
+					if (k[q] == m) k[q] = 0ull;
+			}
+			if (threadIdx.x == 0) top[it] = m;
+		}
 	}
 	__syncthreads();
+	dbg_stamp(F, 2);
 	if (F.world > 1) {
 		// multi-GPU: publish the local candidates (key + complete shooter record) to every rank; the cache is
 		// rebuilt by predict_merge_kernel from the union
@@ -263,13 +289,17 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		}
 	}
 	__syncthreads();
+	dbg_stamp(F, 3);
 	const int nt = s_ntodo;
 	if (threadIdx.x < nt) {	// K2 for the new rows, one thread each
 		const int row = F.todo[threadIdx.x];
 		build_shooter(S, S.slot_to_recv[F.row_slot[row]], &F.rec[row]);
 	}
 	__syncthreads();
+	dbg_stamp(F, 4);
 	build_row_masks(S, F, nt);
+	__syncthreads();
+	dbg_stamp(F, 5);
 }
 
 // Multi-GPU second half of the prediction (one CTA of 256 threads): wait for every rank's candidates,
