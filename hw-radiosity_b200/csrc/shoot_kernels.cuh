@@ -80,13 +80,13 @@ __device__ __forceinline__ unsigned long long make_key(float delta, int slot) {
 	return ((unsigned long long)ordered_bits(delta) << 32) | (unsigned)slot;
 }
 
+// warp-wide maximum of 64-bit keys with two redux.sync instructions: maximum of the high words, then
+// maximum of the low words among the lanes that hold that high word
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
-		k = other > k ? other : k;
-	}
-	return k;
+	const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+	const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+	const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+	return ((unsigned long long)mh << 32) | ml;
 }
 
 // K2: derive the shooter record of receiver r (one thread).
