@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastStat
 constexpr int kFFBlock = 256;
 constexpr int kFFItems = 4;	// candidate vertices per thread before compaction
 
-__global__ void __launch_bounds__(kFFBlock, 4) ff_batch_kernel(DevScene S, FastState F) {
+__global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastState F) {
 	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;
