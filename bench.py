@@ -264,12 +264,14 @@ def run_ours(args):
         ctx.rewind()
 
         # end-to-end through the C ABI with host buffers: state upload + loop + download
+        host_out = ctx.download()            # caller-owned host buffers, reused every step
+
         def e2e_step():
             barrier()
             t = time.perf_counter()
             ctx.reset(model)                 # H2D: accB/deltaB of this rank's receivers from the host TriStore image
             ctx.step(cap)
-            ctx.download()                   # D2H: accB/deltaB of this rank's receivers
+            ctx.download(out=host_out)       # D2H: accB/deltaB of this rank's receivers into the host buffers
             return max_over_ranks(time.perf_counter() - t)
         for _ in range(2):
             e2e_step()

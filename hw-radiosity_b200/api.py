@@ -292,11 +292,15 @@ class Context:
     def trinum(self):
         return load_library().radk_ctx_trinum(self._h)
 
-    def download(self):
+    def download(self, out=None):
+        """Per-slot (accB[n,3,3], deltaB[n,3], parent[n]); pass a previous result as `out` to reuse its buffers."""
         n = self.trinum
-        accB = np.zeros((n, 3, 3), dtype=np.float32)
-        deltaB = np.zeros((n, 3), dtype=np.float32)
-        parent = np.full(n, -1, dtype=np.int32)
+        if out is not None and len(out[0]) == n:
+            accB, deltaB, parent = out
+        else:
+            accB = np.zeros((n, 3, 3), dtype=np.float32)
+            deltaB = np.zeros((n, 3), dtype=np.float32)
+            parent = np.full(n, -1, dtype=np.int32)
         _check(load_library().radk_ctx_download(self._h, accB.ctypes.data, deltaB.ctypes.data, parent.ctypes.data, n))
         return accB, deltaB, parent
 

@@ -110,6 +110,7 @@ struct radk_ctx {
 	DevScene S{};
 	struct HostFlags { int ncand, nsrc, converged; } *h_flags = nullptr;	// pinned
 	long long *h_shots = nullptr;		// pinned
+	float4 *h_stage = nullptr;		// pinned staging for the state planes: 3 x R float4
 	bool use_dedup = true;
 	// adaptive-split mode (split_kernels.cuh): slot-indexed pool instead of the sorted receiver planes
 	bool split_mode = false;
@@ -558,6 +559,7 @@ void radk_ctx_destroy(radk_ctx *c) {
 	}
 	if (c->h_flags) cudaFreeHost(c->h_flags);
 	if (c->h_shots) cudaFreeHost(c->h_shots);
+	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->h_budget) cudaFreeHost(c->h_budget);
 	if (c->h_error) cudaFreeHost(c->h_error);
 	for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
@@ -572,15 +574,15 @@ int radk_ctx_reset(radk_ctx *c, const radk_scene *s) {
 	if (!c || !s) { set_error("radk_ctx_reset: null argument"); return RADK_ERR_ARG; }
 	if (s->trinum != c->trinum) { set_error("radk_ctx_reset: scene size changed"); return RADK_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
-	std::vector<float4> stt(c->R);
+	if (!c->h_stage) CUDA_TRY(cudaMallocHost((void **)&c->h_stage, 3 * (size_t)std::max(c->R, 1) * sizeof(float4)));
+	const size_t R = (size_t)c->R;
+	for (size_t r = 0; r < R; r++) {	// gather from the caller's TriStore image into pinned planes
+		const radk_triangle &t = s->tri[c->recv_slot[r]];
+		for (int v = 0; v < 3; v++) c->h_stage[v * R + r] = make_float4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
+	}
 	for (int v = 0; v < 3; v++) {
-		for (int r = 0; r < c->R; r++) {
-			const radk_triangle &t = s->tri[c->recv_slot[r]];
-			stt[r] = make_float4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
-		}
-		CUDA_TRY(cudaMemcpyAsync(c->st[v].p, stt.data(), (size_t)c->R * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(c->st0[v].p, c->st[v].p, (size_t)c->R * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->st[v].p, c->h_stage + v * R, R * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->st0[v].p, c->st[v].p, R * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
 	}
 	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), c->stream));
@@ -814,22 +816,19 @@ int radk_ctx_download(radk_ctx *c, float *accB, float *deltaB, int *parent, int 
 		}
 		return RADK_OK;
 	}
-	std::vector<float4> h[3];
-	for (int v = 0; v < 3; v++) {
-		h[v].resize(c->R);
-		CUDA_TRY(cudaMemcpyAsync(h[v].data(), c->st[v].p, (size_t)c->R * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-	}
+	if (!c->h_stage) CUDA_TRY(cudaMallocHost((void **)&c->h_stage, 3 * (size_t)std::max(c->R, 1) * sizeof(float4)));
+	const size_t R = (size_t)c->R;
+	for (int v = 0; v < 3; v++)
+		CUDA_TRY(cudaMemcpyAsync(c->h_stage + v * R, c->st[v].p, R * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	for (int r = 0; r < c->R; r++) {
-		const int slot = c->recv_slot[r];
-		for (int v = 0; v < 3; v++) {
-			if (accB) {
-				accB[(size_t)slot * 9 + v * 3 + 0] = h[v][r].x;
-				accB[(size_t)slot * 9 + v * 3 + 1] = h[v][r].y;
-				accB[(size_t)slot * 9 + v * 3 + 2] = h[v][r].z;
-			}
-			if (deltaB) deltaB[(size_t)slot * 3 + v] = h[v][r].w;
+	for (size_t r = 0; r < R; r++) {
+		const size_t slot = (size_t)c->recv_slot[r];
+		const float4 a0 = c->h_stage[r], a1 = c->h_stage[R + r], a2 = c->h_stage[2 * R + r];
+		if (accB) {
+			float *a = accB + slot * 9;
+			a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a1.x, a[4] = a1.y, a[5] = a1.z, a[6] = a2.x, a[7] = a2.y, a[8] = a2.z;
 		}
+		if (deltaB) deltaB[slot * 3] = a0.w, deltaB[slot * 3 + 1] = a1.w, deltaB[slot * 3 + 2] = a2.w;
 		if (parent) parent[slot] = c->recv_parent[r];
 	}
 	return RADK_OK;

@@ -252,9 +252,15 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 	const int U = (int)ukeys.size();
 	F.U = U;
 	std::vector<uint64_t> ukey2(U);
-	for (int u = 0; u < U; u++) {
-		const float p[3] = {upos[u].x, upos[u].y, upos[u].z};
-		ukey2[u] = ((uint64_t)(uint32_t)ukeys[u].parent << 32) | morton(p);
+	// order: start leaf of the vertex's rays (every ray begins in the leaf that contains the vertex, so a warp's
+	// lanes scan the same triangle list in their first - often only - leaf visit), then Morton code inside the leaf
+	{
+		const DevTree T = F.host_tree(s);
+		for (int u = 0; u < U; u++) {
+			const float p[3] = {upos[u].x, upos[u].y, upos[u].z};
+			const int leaf = leaf_of<false>(T, p[0], p[1], p[2], nullptr);
+			ukey2[u] = ((uint64_t)(uint32_t)(leaf + 1) << 32) | morton(p);
+		}
 	}
 	std::vector<int> uorder(U), unew(U);
 	std::iota(uorder.begin(), uorder.end(), 0);
