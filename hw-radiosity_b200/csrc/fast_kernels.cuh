@@ -254,11 +254,27 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		if (threadIdx.x < rows) {
 			PredCand pc;
 			pc.key = top[threadIdx.x], pc.pad[0] = pc.pad[1] = 0;
-			if (pc.key != 0ull) build_shooter(S, S.slot_to_recv[(int)(pc.key & 0xffffffffu)], &pc.rec);
-			else pc.rec.valid = 0;
-			for (int t = 0; t < F.world; t++) peer_copy(&F.box[t]->pred[par][F.rank][threadIdx.x], &pc, (int)sizeof(PredCand));
-			__threadfence_system();
+			pc.rec.valid = 0;
+			// the record only travels when no rank has it yet (the caches are identical on all ranks)
+			const bool fresh = pc.key != 0ull && F.slot_row[(int)(pc.key & 0xffffffffu)] < 0;
+			if (fresh) build_shooter(S, S.slot_to_recv[(int)(pc.key & 0xffffffffu)], &pc.rec);
+			for (int t = 0; t < F.world; t++) {
+				PredCand *dst = &F.box[t]->pred[par][F.rank][threadIdx.x];
+				if (fresh) {
+					peer_copy(dst, &pc, (int)sizeof(PredCand));
+				} else {	// key + current unshot energy (the handoff needs it if this candidate is the global best)
+					*((volatile unsigned long long *)&dst->key) = pc.key;
+					if (pc.key != 0ull) {
+						const int r = S.slot_to_recv[(int)(pc.key & 0xffffffffu)];
+						*((volatile float *)&dst->rec.dB[0]) = S.st[0][r].w;
+						*((volatile float *)&dst->rec.dB[1]) = S.st[1][r].w;
+						*((volatile float *)&dst->rec.dB[2]) = S.st[2][r].w;
+					}
+				}
+			}
 		}
+		__syncthreads();
+		if (threadIdx.x == 0) __threadfence_system();	// cumulative: orders the CTA's mail before the sequence numbers
 		__syncthreads();
 		if (threadIdx.x < F.world)
 			*((volatile unsigned long long *)&F.box[threadIdx.x]->pred_seq[par][F.rank]) = (F.epoch << 40) | s_round;
