@@ -62,7 +62,7 @@ EXPORTS = [
     "radk_default_opts", "radk_last_error", "radk_version", "radk_default_model_opts", "radk_model_load",
     "radk_model_parse", "radk_model_free", "radk_model_scene", "radk_model_sample_area", "radk_model_min_area",
     "radk_model_max_area", "radk_model_triangles", "radk_model_set_triangles", "radk_model_dump",
-    "radk_model_write", "radk_model_format", "radk_ctx_create", "radk_ctx_destroy", "radk_ctx_reset",
+    "radk_model_write", "radk_model_write_colors", "radk_model_write_wait", "radk_model_format", "radk_ctx_create", "radk_ctx_destroy", "radk_ctx_reset",
     "radk_ctx_rewind", "radk_ctx_step", "radk_ctx_select", "radk_ctx_shoot", "radk_ctx_shooter_log", "radk_ctx_trinum",
     "radk_ctx_download", "radk_ctx_download_triangles", "radk_ctx_snapshot_colors", "radk_ctx_stats",
     "radk_ctx_device_ms", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_vertex_ff",
@@ -110,6 +110,8 @@ def load_library():
     L.radk_model_set_triangles.argtypes = [vp, vp, C.c_int]
     L.radk_model_dump.argtypes = [vp, C.POINTER(Opts), C.c_char_p]
     L.radk_model_write.argtypes = [vp, C.c_char_p, C.c_int]
+    L.radk_model_write_colors.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_int]
+    L.radk_model_write_wait.argtypes = [vp]
     L.radk_model_format.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.radk_ctx_create.argtypes = [C.POINTER(SceneStruct), C.POINTER(Opts), C.POINTER(vp)]
     L.radk_ctx_destroy.argtypes = [vp]
@@ -224,6 +226,13 @@ class Model:
 
     def write(self, prefix, loop=0):
         _check(load_library().radk_model_write(self._h, os.fsencode(prefix), loop))
+
+    def write_colors(self, prefix, rgb, loop=0, wait=True):
+        """Background snapshot from per-slot colours (Context.snapshot_colors()), cached geometry text."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.int32)
+        _check(load_library().radk_model_write_colors(self._h, os.fsencode(prefix), loop, rgb.ctypes.data, len(rgb)))
+        if wait:
+            _check(load_library().radk_model_write_wait(self._h))
 
     def format(self):
         n = C.c_size_t()

@@ -71,8 +71,69 @@ static inline void snapshot_rgb(const radk_triangle &t, int rgb[3]) {	// rad.cpp
 	}
 }
 
+static char token[64] = {0};	// the reference's static conversion buffer survives across calls
+
+// The three "x y z nx ny nz" lines of one leaf (rad.cpp:181-219), appended to out.
+static void append_geometry(const radk_triangle &t, std::string &out) {
+	std::string normal;
+	for (int k = 0; k < 3; k++) {
+		float_to_text(t.n[k], token);
+		normal += token;
+		normal += (k < 2) ? " " : "\n";
+	}
+	for (int v = 0; v < 3; v++) {
+		for (int k = 0; k < 3; k++) {
+			float_to_text(t.p[v][k], token);
+			out += token;
+			out += ' ';
+		}
+		out += normal;
+	}
+}
+
+void build_geometry_cache(Model &m) {
+	m.geom_text.clear();
+	m.geom_off.clear();
+	m.geom_slot.clear();
+	m.geom_text.reserve((size_t)m.trinum * 60);
+	for (int i = 0; i < m.trinum; i++) {
+		const radk_triangle &t = m.tri[i];
+		if (t.parent < 0) continue;
+		m.geom_off.push_back(m.geom_text.size());
+		m.geom_slot.push_back(i);
+		append_geometry(t, m.geom_text);
+	}
+	m.geom_off.push_back(m.geom_text.size());
+	m.geom_valid = true;
+}
+
+static inline char *put_int(char *d, int v) {	// "%d"
+	if (v < 0) { *d++ = '-'; v = -v; }
+	char tmp[12];
+	int n = 0;
+	do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+	while (n) *d++ = tmp[--n];
+	return d;
+}
+
+void format_fin_colors(const Model &m, const int *rgb, std::string &out) {
+	const size_t leaves = m.geom_slot.size();
+	out.resize(m.geom_text.size() + leaves * 64);
+	char *d = &out[0];
+	for (size_t k = 0; k < leaves; k++) {
+		memcpy(d, "Triangle \n", 10), d += 10;
+		const int *c = rgb + (size_t)m.geom_slot[k] * 3;
+		d = put_int(d, c[0]), *d++ = ' ';
+		d = put_int(d, c[1]), *d++ = ' ';
+		d = put_int(d, c[2]);
+		memcpy(d, " 0 0 0\n", 7), d += 7;
+		const size_t len = m.geom_off[k + 1] - m.geom_off[k];
+		memcpy(d, m.geom_text.data() + m.geom_off[k], len), d += len;
+	}
+	out.resize((size_t)(d - &out[0]));
+}
+
 void format_fin(const Model &m, std::string &out) {
-	static char token[64] = {0};	// the reference's static conversion buffer survives across calls
 	out.clear();
 	out.reserve((size_t)m.trinum * 120);
 	char line[160];
@@ -84,20 +145,7 @@ void format_fin(const Model &m, std::string &out) {
 		snapshot_rgb(t, rgb);
 		int n = snprintf(line, sizeof(line), "%d %d %d 0 0 0\n", rgb[0], rgb[1], rgb[2]);
 		out.append(line, n);
-		std::string normal;
-		for (int k = 0; k < 3; k++) {
-			float_to_text(t.n[k], token);
-			normal += token;
-			normal += (k < 2) ? " " : "\n";
-		}
-		for (int v = 0; v < 3; v++) {
-			for (int k = 0; k < 3; k++) {
-				float_to_text(t.p[v][k], token);
-				out += token;
-				out += ' ';
-			}
-			out += normal;
-		}
+		append_geometry(t, out);
 	}
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 #include "radk.h"
 
@@ -29,6 +30,14 @@ struct Model {
 	int grid_num = 0;
 	float min_area = 0, max_area = 0, sample_area = -1;
 	radk_model_opts opts{};
+	// snapshot writer state (fin_writer.cpp): the vertex/normal text of a frozen mesh never changes, so it is
+	// formatted once; a snapshot then only needs one colour line per leaf
+	std::string geom_text;			// concatenated "x y z nx ny nz\n" x3 chunks of all leaves, slot order
+	std::vector<size_t> geom_off;		// chunk boundaries (leaves + 1 entries)
+	std::vector<int> geom_slot;		// slot of each leaf
+	bool geom_valid = false;
+	std::thread writer;			// at most one snapshot file being written in the background
+	int writer_rc = 0;
 
 	int pool_limit() const {
 		int mt = opts.max_tri > 0 ? opts.max_tri : kRefMaxTri;
@@ -52,6 +61,9 @@ void init_radiosity(Model &m);
 void prepartition(Model &m);
 // fin_writer.cpp  (rad.cpp:117-221 + float2string.h)
 void format_fin(const Model &m, std::string &out);
+void build_geometry_cache(Model &m);
+// text of a snapshot from per-slot colours rgb[trinum][3] (logical slots ignored) and the cached geometry
+void format_fin_colors(const Model &m, const int *rgb, std::string &out);
 int float_to_text(float v, char *buf);	// fp::tostring<float> equivalent; returns length, 0 = nothing written
 
 }  // namespace radk

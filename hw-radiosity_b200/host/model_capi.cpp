@@ -68,7 +68,10 @@ int radk_model_load(const char *tri_path, const radk_model_opts *o, radk_model *
 	return radk_model_parse(text.data(), text.size(), o, out);
 }
 
-void radk_model_free(radk_model *m) { delete m; }
+void radk_model_free(radk_model *m) {
+	if (m && m->m.writer.joinable()) m->m.writer.join();
+	delete m;
+}
 
 int radk_model_scene(const radk_model *h, radk_scene *out) {
 	if (!h || !out) { radk::set_error("radk_model_scene: null argument"); return RADK_ERR_ARG; }
@@ -98,8 +101,10 @@ radk_triangle *radk_model_triangles(radk_model *h, int *trinum) {
 
 int radk_model_set_triangles(radk_model *h, const radk_triangle *tri, int trinum) {
 	if (!h || !tri || trinum < 0) { radk::set_error("radk_model_set_triangles: bad argument"); return RADK_ERR_ARG; }
+	if (h->m.writer.joinable()) h->m.writer.join();
 	h->m.tri.assign(tri, tri + trinum);
 	h->m.trinum = trinum;
+	h->m.geom_valid = false;
 	return RADK_OK;
 }
 
@@ -136,6 +141,40 @@ int radk_model_dump(const radk_model *h, const radk_opts *o, const char *path) {
 	fwrite(m.list.data(), sizeof(int), m.list.size(), f);
 	fclose(f);
 	return RADK_OK;
+}
+
+int radk_model_write_wait(radk_model *h) {
+	if (!h) { radk::set_error("radk_model_write_wait: null argument"); return RADK_ERR_ARG; }
+	if (h->m.writer.joinable()) h->m.writer.join();
+	const int rc = h->m.writer_rc;
+	h->m.writer_rc = 0;
+	if (rc) radk::set_error("output file open failed");
+	return rc;
+}
+
+int radk_model_write_colors(radk_model *h, const char *prefix, int loop, const int *rgb, int trinum) {
+	if (!h || !prefix || !rgb) { radk::set_error("radk_model_write_colors: null argument"); return RADK_ERR_ARG; }
+	radk::Model &m = h->m;
+	if (trinum != m.trinum) { radk::set_error("radk_model_write_colors: colour array does not match the model"); return RADK_ERR_ARG; }
+	const int prev = radk_model_write_wait(h);
+	if (!m.geom_valid) radk::build_geometry_cache(m);
+	std::string fn(prefix);
+	if (loop == 0) fn += ".fin";
+	else fn += "." + std::to_string(loop);
+	std::string text;
+	radk::format_fin_colors(m, rgb, text);
+	m.writer = std::thread([&m, fn, loop, text = std::move(text)]() {
+		FILE *f = fopen(fn.c_str(), "w");
+		if (!f) {	// rad.cpp:131-138
+			fprintf(stderr, "Error: output file %s open failed\n", fn.c_str());
+			if (loop != 0) { m.writer_rc = RADK_ERR_IO; return; }
+			fwrite(text.data(), 1, text.size(), stdout);
+			return;
+		}
+		fwrite(text.data(), 1, text.size(), f);
+		fclose(f);
+	});
+	return prev;
 }
 
 int radk_model_format(const radk_model *h, char *buf, size_t cap, size_t *len) {

@@ -159,21 +159,20 @@ bool write_snapshot(radk_ctx *ctx, radk_model *model, const Options &o, int loop
 		after_write(o, std::string(o.prefix) + (loop == 0 ? std::string(".fin") : "." + std::to_string(loop)));
 		return true;
 	}
-	int trinum = 0;
-	radk_triangle *tri = radk_model_triangles(model, &trinum);
-	std::vector<float> acc((size_t)trinum * 9), dB((size_t)trinum * 3);
-	std::vector<int> parent((size_t)trinum, -1);
-	if (radk_ctx_download(ctx, acc.data(), dB.data(), parent.data(), trinum) != RADK_OK) {
+	// frozen mesh: colours are reduced on the device (K5), the geometry text is cached, the file is written by a
+	// background thread.  -zip / -interactive act on the finished file, so they wait for it.
+	const int trinum = radk_ctx_trinum(ctx);
+	static std::vector<int> rgb;
+	rgb.resize((size_t)trinum * 3);
+	if (radk_ctx_snapshot_colors(ctx, rgb.data(), trinum) != RADK_OK) {
 		fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
 		return false;
 	}
-	for (int i = 0; i < trinum; i++) {
-		if (parent[i] < 0) continue;
-		memcpy(tri[i].accB, &acc[(size_t)i * 9], 36);
-		memcpy(tri[i].deltaB, &dB[(size_t)i * 3], 12);
+	radk_model_write_colors(model, o.prefix, loop, rgb.data(), trinum);
+	if (o.zip || o.interactive || loop == 0) {
+		if (radk_model_write_wait(model) != RADK_OK) return loop != 0;
+		after_write(o, std::string(o.prefix) + (loop == 0 ? std::string(".fin") : "." + std::to_string(loop)));
 	}
-	if (radk_model_write(model, o.prefix, loop) != RADK_OK) return loop != 0;
-	after_write(o, std::string(o.prefix) + (loop == 0 ? std::string(".fin") : "." + std::to_string(loop)));
 	return true;
 }
 

@@ -147,6 +147,12 @@ int radk_model_set_triangles(radk_model *m, const radk_triangle *tri, int trinum
 int radk_model_dump(const radk_model *m, const radk_opts *o, const char *path);
 /* PrintOut (rad.cpp:117-242) body: "<prefix>.fin" when loop == 0 else "<prefix>.<loop>". */
 int radk_model_write(const radk_model *m, const char *prefix, int loop);
+/* Snapshot writer for a frozen mesh: same file as radk_model_write, but from per-slot
+ * colours rgb[trinum][3] (radk_ctx_snapshot_colors) instead of the model's accB; the vertex/normal text is
+ * formatted once and reused, and the file is written by a background thread (at most one in flight; the
+ * next call, radk_model_write_wait or radk_model_free joins it).  Returns the previous write's status. */
+int radk_model_write_colors(radk_model *m, const char *prefix, int loop, const int *rgb, int trinum);
+int radk_model_write_wait(radk_model *m);
 /* The same text into a caller buffer; returns the needed size in *len. */
 int radk_model_format(const radk_model *m, char *buf, size_t cap, size_t *len);
 

@@ -89,3 +89,20 @@ def test_writer_number_formatting(hr):
     assert lines[2].split()[:3] == ["0.0", "-0.0", "0.0"]
     assert lines[3].split()[:3] == ["123456.7890625", "-0.00012345", "3.14159274"]
     assert lines[4].split()[:3] == ["16777216.0", "1000000000.0", "-2.5"]
+
+
+def test_colour_snapshot_writer_equals_plain_writer(hr, po, models_dir, tmp_path):
+    """radk_model_write_colors (cached geometry text + colour lines, background thread) writes the same bytes as
+    the PrintOut restatement, for several snapshots in a row."""
+    from conftest import oracle_scene
+    m = hr.Model(str(models_dir / "model3s.tri"))
+    sc = oracle_scene(po, m)
+    for loop in (10, 20, 0):
+        sc.run(10)
+        m.set_triangles(sc.slots)
+        want = m.format()
+        rgb = sc.snapshot_colors()
+        rgb[sc.slots["parent"] < 0] = -1
+        m.write_colors(str(tmp_path / "snap"), rgb, loop=loop)
+        name = "snap.fin" if loop == 0 else f"snap.{loop}"
+        assert (tmp_path / name).read_bytes() == want
