@@ -1,0 +1,110 @@
+"""Edge cases of the loop on the GPU against the oracle: nothing to shoot, tiny scenes, an emitter too
+small to be split (AdaptCalFF's `maxlength < 0.1` exit, shade.cpp:154-155), thresholds at and below zero,
+more parallel sources than candidates, a saturating light scale, non-power-of-two grids."""
+import numpy as np
+import pytest
+
+from conftest import oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+ROOM = """Triangle
+200 200 200 0 0 0
+0 0 0
+40 0 0
+40 40 0
+Triangle
+200 200 200 0 0 0
+0 0 0
+40 40 0
+0 40 0
+Triangle
+150 100 50 0 0 0
+0 0 30
+40 40 30
+40 0 30
+Triangle
+150 100 50 0 0 0
+0 0 30
+0 40 30
+40 40 30
+"""
+
+
+def light(size, z=15.0, cx=20.0, cy=20.0, rgb="255 255 255"):
+    a, b = cx - size / 2, cx + size / 2
+    c, d = cy - size / 2, cy + size / 2
+    return (f"Triangle\n{rgb} {rgb}\n{a} {c} {z}\n{b} {c} {z}\n{b} {d} {z}\n"
+            f"Triangle\n{rgb} {rgb}\n{a} {c} {z}\n{b} {d} {z}\n{a} {d} {z}\n")
+
+
+def compare(hr, po, text, shots=-1, model_kw=None, **ctx_kw):
+    m = hr.Model(text=text.encode(), **(model_kw or {}))
+    okw = {k: v for k, v in ctx_kw.items() if k in ("converge", "parallel_src")}
+    sc = oracle_scene(po, m, **okw)
+    seq = sc.run(None if shots < 0 else shots)
+    live = sc.slots["parent"] >= 0
+    for extra in ({}, {"collect_stats": 1}):
+        ctx = hr.Context(m, **ctx_kw, **extra)
+        done, conv = ctx.step(shots)
+        assert done == len(seq)
+        assert ctx.shooter_log() == [s[0] for s in seq]
+        acc, dB, _ = ctx.download()
+        assert np.array_equal(acc[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
+        assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
+        if extra:
+            st = ctx.stats()
+            assert (st["rays"], st["visible"]) == (sc.stats["rays"], sc.stats["visible"])
+    return len(seq), m
+
+
+def test_no_emitter_converges_immediately(hr, po):
+    n, m = compare(hr, po, ROOM)
+    assert n == 0
+    ctx = hr.Context(m)
+    assert ctx.step(-1) == (0, True) and ctx.step(5) == (0, True)
+
+
+def test_small_scene_to_convergence(hr, po):
+    n, _ = compare(hr, po, ROOM + light(8.0))
+    assert n > 3
+
+
+def test_emitter_too_small_to_split(hr, po):
+    # longest edge^2 = 2 * 0.2^2 = 0.08 < 0.1: the centre sample alone is used (single ray per vertex)
+    n, _ = compare(hr, po, ROOM + light(0.2), shots=6)
+    assert n >= 2
+
+
+def test_zero_and_negative_threshold(hr, po):
+    compare(hr, po, ROOM + light(8.0), shots=40, converge=0.0)
+    compare(hr, po, ROOM + light(8.0), shots=40, converge=-5.0)      # spent shooters (delta 0) stay candidates
+
+
+def test_more_parallel_sources_than_candidates(hr, po):
+    compare(hr, po, ROOM + light(8.0), shots=12, parallel_src=50)
+
+
+def test_dim_and_saturating_lights(hr, po):
+    compare(hr, po, ROOM + light(8.0), shots=10, model_kw={"light": 0.25})
+    compare(hr, po, ROOM + light(8.0), shots=10, model_kw={"light": 3.0})
+
+
+def test_synthetic_room_non_power_of_two_grid(hr, po):
+    from hw_radiosity_b200 import synth
+    text = synth.room_scene(1000000, seed=1)
+    m = hr.Model(text=text, tri_limit=3000000, max_tri=3000000)
+    assert m.scene.grid_num not in (1, 2, 4, 8, 16, 32, 64)          # exercises the generic cell table
+    sc = oracle_scene(po, m, converge=1.0)
+    seq = sc.run(3)
+    ctx = hr.Context(m, converge=1.0, collect_stats=1)
+    assert ctx.step(3)[0] == len(seq) and ctx.shooter_log() == [s[0] for s in seq]
+    live = sc.slots["parent"] >= 0
+    acc, dB, _ = ctx.download()
+    assert np.array_equal(acc[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
+    st = ctx.stats()
+    assert (st["rays"], st["visible"]) == (sc.stats["rays"], sc.stats["visible"])
+    fast = hr.Context(m, converge=1.0)
+    fast.step(3)
+    acc2, _, _ = fast.download()
+    assert np.array_equal(acc2[live].view(np.uint32), acc[live].view(np.uint32))
