@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 	// phase 2: every lane walks rays from the queue; a lane whose ray is decided fetches the next one
 	// at the following leaf step, so lanes stay busy although rays visit different numbers of leaves.
 	const DevTree &T = S.tree;
-	int i = -1, u = 0, ban = 0, prev = -1, guard = 0;
+	int i = -1, u = 0, ban = 0, prev = -1, guard = 0, steps = 0;
 	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, qx = 0, qy = 0, qz = 0, t = 0, ffq = 0;
 	for (;;) {
 		if (i < 0) {
@@ -474,11 +474,11 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 			const float4 v = __ldg(&S.uv[u]);
 			px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
 			vx = smp.cx - px, vy = smp.cy - py, vz = smp.cz - pz;
-			qx = px, qy = py, qz = pz, prev = -1, guard = 0, t = 0.f;
+			qx = px, qy = py, qz = pz, prev = -1, guard = 0, steps = 0, t = 0.f;
 		}
 		int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
 		const int cur = leaf_of<false>(T, qx, qy, qz, nullptr);
-		if (cur < 0) {
+		if (cur < 0 || ++steps > kMaxWalkSteps) {
 			verdict = 0;
 		} else if (prev == cur) {		// raycast.cpp:344-351
 			t = (float)((double)t + 1.0);

@@ -47,6 +47,11 @@ struct DevTree {
 //   q0 = n.x n.y n.z c.x | q1 = c.y c.z se00 se01 | q2 = se02 se03 se10 se11
 //   q3 = se12 se13 se20 se21 | q4 = se22 se23 - -
 constexpr int OCC_STRIDE = 5;
+// A walk visits at most ~3 * grid_num leaves.  When GridNum is not a power of two (float rounding of
+// (G1-G0)/MinGridLen, e.g. 63) the reference's cell -> leaf descent disagrees with the leaf boxes and its
+// RayHitted can bounce between two leaves forever; the walk is cut after this many leaf lookups and the
+// ray counts as leaving the scene (the oracle applies the same cut, the reference itself would hang).
+constexpr int kMaxWalkSteps = 1024;
 
 struct WalkCounters {
 	unsigned traced, leaf_visits, descent_steps, tri_tests, tri_accepts, precision_exceeded, guard_trips;
@@ -139,9 +144,13 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 	float t = 0.f;
 	int prev = -1, cur;
 	float qx = px, qy = py, qz = pz;
-	int guard = 0;
+	int guard = 0, steps = 0;
 	if (STATS) wc->traced++;
 	while ((cur = leaf_of<STATS>(T, qx, qy, qz, wc)) >= 0) {
+		if (++steps > kMaxWalkSteps) {
+			if (STATS) wc->guard_trips++;
+			return -1;
+		}
 		if (prev == cur) {		// raycast.cpp:344-351 "Precision Exceeded"
 			if (STATS) wc->precision_exceeded++;
 			t = (float)((double)t + 1.0);
@@ -242,8 +251,9 @@ RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, flo
 	float t = 0.f;
 	int prev = -1, cur;
 	float qx = px, qy = py, qz = pz;
-	int guard = 0;
+	int guard = 0, steps = 0;
 	while ((cur = leaf_of<false>(T, qx, qy, qz, nullptr)) >= 0) {
+		if (++steps > kMaxWalkSteps) return false;
 		if (prev == cur) {		// raycast.cpp:344-351
 			t = (float)((double)t + 1.0);
 			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;

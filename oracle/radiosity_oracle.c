@@ -120,9 +120,13 @@ static int ray_hitted(const orc_scene *s, const float *p, const float *v, int fr
 	float t = 0.f;
 	int prev = -1, cur, hit;
 	float q[3] = { p[0], p[1], p[2] };
-	long guard = 0;
+	long guard = 0, steps = 0;
 	(void)to;
 	while ((cur = tree_node_num(s, q, st)) >= 0) {
+		/* Not in the reference: when GridNum is not a power of two its descent disagrees with the leaf boxes
+		 * and this loop can bounce between two leaves forever; cut like the device does (rt_core.cuh kMaxWalkSteps). */
+		if (++steps > 1024)
+			return -1;
 		if (prev == cur) {
 			st->precision_exceeded++;
 			t = (float)((double)t + 1.0);
