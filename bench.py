@@ -190,7 +190,9 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    # stdout carries exactly one JSON line: library chatter (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local_rank = rdist.init("nccl")
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -240,17 +242,23 @@ def run_ours(args):
             assert done == shots_per_step, (done, shots_per_step)
             return max_over_ranks(ctx.device_ms - before)       # device time, max over ranks
 
-        for _ in range(max(args.warmup, 3)):
-            one_step()
-        l0 = ctx.stats()["kernel_launches"]
-        torch.cuda.synchronize()
-        barrier()
+        # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed region (the timed
+        # region alone lasts tens of milliseconds, shorter than one nvidia-smi sampling period)
         with ClockSampler(local_rank) as clk:
+            for _ in range(max(args.warmup, 3)):
+                one_step()
+            l0 = ctx.stats()["kernel_launches"]
+            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             dev_ms = [one_step() for _ in range(args.steps)]
             torch.cuda.synchronize()
             barrier()
             wall = time.perf_counter() - t0
+            if wall < 0.5:                      # keep the GPU under the same load until the sampler has a few readings
+                t_end = time.perf_counter() + 0.6
+                while time.perf_counter() < t_end:
+                    one_step()
         launches = ctx.stats()["kernel_launches"] - l0
         ms_per_step = sum(dev_ms) / len(dev_ms)
         value = rays_per_step / (ms_per_step / 1e3)
@@ -338,7 +346,7 @@ def run_ours(args):
                                 "sample": f"{model_name}, {cpu['shots']} shots, shot loop only ({cpu['seconds']:.2f} s)",
                                 "seconds": cpu["seconds"]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.barrier()
