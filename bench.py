@@ -255,11 +255,11 @@ def run_ours(args):
             torch.cuda.synchronize()
             barrier()
             wall = time.perf_counter() - t0
+            launches = ctx.stats()["kernel_launches"] - l0
             if wall < 0.5:                      # keep the GPU under the same load until the sampler has a few readings
                 t_end = time.perf_counter() + 0.6
                 while time.perf_counter() < t_end:
                     one_step()
-        launches = ctx.stats()["kernel_launches"] - l0
         ms_per_step = sum(dev_ms) / len(dev_ms)
         value = rays_per_step / (ms_per_step / 1e3)
 
