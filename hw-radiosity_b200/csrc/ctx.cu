@@ -72,10 +72,7 @@ struct radk_ctx {
 
 	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot, leaf_list4, tri_leaf_begin, tri_leaves;
 	DevBuf<int4> list4;
-	DevBuf<unsigned> row_mask, ray_count;
-	DevBuf<int2> ray_um;
-	DevBuf<float> ray_ff;
-	int walk_ctas = 0;
+	DevBuf<unsigned> row_mask;
 	DevBuf<float4> leaf_lo, leaf_hi, occ, geo[3], st[3], st0[3], uv, par_n, par_fk;
 	DevBuf<int4> vid;
 	DevBuf<float2> ffh;
@@ -157,10 +154,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	if (c->F.world > 1) { predict_merge_kernel<<<1, 256, 0, st>>>(c->S, c->F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
-	CUDA_TRY(cudaMemsetAsync(c->F.ray_count, 0, 2 * sizeof(unsigned), st));
-	ff_cull_kernel<<<g, kFFBlock, 0, st>>>(c->S, c->F);
-	ff_walk_kernel<<<c->walk_ctas, kFFBlock, 0, st>>>(c->S, c->F);
-	c->launches++;
+	ff_batch_kernel<<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	int max_ctas = c->shots_ctas;
 	void *args[] = {(void *)&c->S, (void *)&c->F, (void *)&max_ctas};
@@ -419,16 +413,6 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.barrier = c->fast_uints.p + 1;
 		F.handoff = c->handoff.p, F.partial = c->partial.p, F.budget = c->budget.p;
 		F.row_mask = c->row_mask.p, F.mask_words = mask_words;
-		{
-			const size_t max_rays = (size_t)rows * 2 * std::max(U, 1);
-			CUDA_TRY(c->ray_um.alloc(max_rays));
-			CUDA_TRY(c->ray_ff.alloc(max_rays));
-			CUDA_TRY(c->ray_count.alloc(2));
-			F.ray_um = c->ray_um.p, F.ray_ff = c->ray_ff.p, F.ray_count = c->ray_count.p;
-			int per_sm = 0;
-			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ff_walk_kernel, kFFBlock, 0));
-			c->walk_ctas = dev_sms * std::max(per_sm, 1);
-		}
 		for (int t = 0; t < kMaxWorld; t++) F.box[t] = nullptr;
 		F.box[o.rank] = c->box.p;
 		F.rank = o.rank, F.world = world;

@@ -102,9 +102,6 @@ struct FastState {
 	Partial *partial;		// [2][max CTAs], 32-byte records
 	unsigned *barrier;		// grid barrier counter (zeroed before each shots launch)
 	long long *budget;		// shots the current radk_ctx_step call may still run
-	int2 *ray_um;			// global ray list of a batch: .x = unique vertex, .y = (row << 1) | half
-	float *ray_ff;			//   and the form factor the ray carries if it reaches the shooter
-	unsigned *ray_count;		// [0] rays appended by ff_cull_kernel, [1] rays handed out by ff_walk_kernel
 	unsigned *row_mask;		// [rows][mask_words] bit n set <=> leaf n's list contains the row's logsrc
 	int mask_words;
 	int *stalled;			// 1: shots_kernel stopped on a cache miss
@@ -403,17 +400,19 @@ __global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastStat
 constexpr int kFFBlock = 256;
 constexpr int kFFItems = 4;	// candidate vertices per thread before compaction
 
-// K3a, first half: culls + analytic form factor for (row, half, vertex) items; survivors go to the batch's ray list.
-__global__ void __launch_bounds__(kFFBlock) ff_cull_kernel(DevScene S, FastState F) {
+__global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastState F) {
+	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;
 	const int row = F.todo[j], half = blockIdx.y;
 	__shared__ ShooterRec sh;
 	__shared__ int q_u[kFFBlock * kFFItems];
 	__shared__ float q_ff[kFFBlock * kFFItems];
-	__shared__ int s_next, s_total;
+	__shared__ int wcount[kFFItems * (kFFBlock / 32)];
+	__shared__ int s_next;
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)(F.rec + row))[threadIdx.x];
-	if (threadIdx.x == 0) s_next = 0, s_total = 0;
+	for (int w = threadIdx.x; w < F.mask_words; w += kFFBlock) s_mask[w] = F.row_mask[(size_t)row * F.mask_words + w];
+	if (threadIdx.x == 0) s_next = 0;
 	__syncthreads();
 	float2 *out = F.ff + (size_t)row * S.U;
 	const int base = blockIdx.x * (kFFBlock * kFFItems);
@@ -426,127 +425,96 @@ __global__ void __launch_bounds__(kFFBlock) ff_cull_kernel(DevScene S, FastState
 		return;
 	}
 	const FFSample smp = sh.splittable ? sh.half[half] : sh.centre;
-	// phase 1: culls + analytic form factor; survivors are appended to the CTA's queue (one shared-memory atomic
-	// per warp and 32 vertices, so neighbouring vertices stay neighbours in the queue)
+	const int logsrc = sh.logsrc;
+	// phase 1: culls + analytic form factor; survivors are queued in vertex order
+	float ffv[kFFItems];
+	bool live[kFFItems];
+	unsigned ball[kFFItems];
+#pragma unroll
 	for (int it = 0; it < kFFItems; it++) {
 		const int u = base + it * kFFBlock + threadIdx.x;
-		bool live = false;
-		float ffv = 0.0f;
+		live[it] = false, ffv[it] = 0.0f;
 		if (u < S.U) {
 			const float4 v = __ldg(&S.uv[u]);
 			const float4 pn = __ldg(&S.par_n[__float_as_int(v.w)]);
 			float dx, dy, dz;
-			ffv = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live);
-			if (!live) { if (half) out[u].y = 0.0f; else out[u].x = 0.0f; }
+			ffv[it] = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live[it]);
+			if (!live[it]) { if (half) out[u].y = 0.0f; else out[u].x = 0.0f; }
 		}
-		const unsigned ball = __ballot_sync(0xffffffffu, live);
-		int wbase = 0;
-		if (lane == 0 && ball) wbase = atomicAdd(&s_total, __popc(ball));
-		wbase = __shfl_sync(0xffffffffu, wbase, 0);
-		if (live) {
-			const int pos = wbase + __popc(ball & ((1u << lane) - 1u));
-			q_u[pos] = u;
-			q_ff[pos] = ffv;
+		ball[it] = __ballot_sync(0xffffffffu, live[it]);
+		if (lane == 0) wcount[it * (kFFBlock / 32) + warp] = __popc(ball[it]);
+	}
+	__syncthreads();
+	int total = 0;
+#pragma unroll
+	for (int it = 0; it < kFFItems; it++) {
+		int off = 0;
+		for (int w = 0; w < kFFItems * (kFFBlock / 32); w++) {
+			const int c = wcount[w];
+			if (w < it * (kFFBlock / 32) + warp) off += c;
+			if (it == 0) total += c;
+		}
+		if (live[it]) {
+			const int pos = off + __popc(ball[it] & ((1u << lane) - 1u));
+			q_u[pos] = base + it * kFFBlock + threadIdx.x;
+			q_ff[pos] = ffv[it];
 		}
 	}
 	__syncthreads();
-	const int total = s_total;
-	// hand the survivors to the walkers: one global reservation per CTA, coalesced copy
-	__shared__ unsigned s_gbase;
-	if (threadIdx.x == 0) s_gbase = total ? atomicAdd(&F.ray_count[0], (unsigned)total) : 0u;
-	__syncthreads();
-	for (int i = threadIdx.x; i < total; i += kFFBlock) {
-		F.ray_um[s_gbase + i] = make_int2(q_u[i], (row << 1) | half);
-		F.ray_ff[s_gbase + i] = q_ff[i];
-	}
-}
-
-// K3a, second half: persistent walkers.  Every warp takes rays from the batch's global list 64 at a time and
-// every lane that has decided its ray takes the next one at the following leaf step, so the lanes stay busy
-// although rays visit 1-10 leaves, and neither CTA tails nor wave quantisation are left (the list is consumed
-// by whichever warp is free).  Rays of different cache rows can share a warp: each lane carries its own
-// target point and looks its row's leaf mask up through L1.
-__global__ void __launch_bounds__(kFFBlock, 5) ff_walk_kernel(DevScene S, FastState F) {
+	// phase 2: every lane walks rays from the queue; a lane whose ray is decided fetches the next one
+	// at the following leaf step, so lanes stay busy although rays visit different numbers of leaves.
 	const DevTree &T = S.tree;
-	const unsigned nrays = F.ray_count[0];
-	const int lane = threadIdx.x & 31;
-	unsigned chunk_lo = 0, chunk_hi = 0;	// warp-uniform: rays [chunk_lo, chunk_hi) belong to this warp
-	int have = 0, u = 0, row = 0, half = 0, ban = 0, prev = -1, guard = 0, steps = 0, logsrc = 0;
+	int i = -1, u = 0, ban = 0, prev = -1, guard = 0, steps = 0;
 	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, qx = 0, qy = 0, qz = 0, t = 0, ffq = 0;
-	bool drained = false;
 	for (;;) {
-		// refill idle lanes from the warp's chunk; fetch a new chunk when it is used up
-		unsigned idle = __ballot_sync(0xffffffffu, !have);
-		while (idle && !drained) {
-			if (chunk_lo == chunk_hi) {
-				unsigned lo = 0;
-				if (lane == 0) lo = atomicAdd(&F.ray_count[1], 64u);
-				lo = __shfl_sync(0xffffffffu, lo, 0);
-				if (lo >= nrays) { drained = true; break; }
-				chunk_lo = lo, chunk_hi = min(lo + 64u, nrays);
-			}
-			const unsigned rank = __popc(idle & ((1u << lane) - 1u));
-			const unsigned avail = chunk_hi - chunk_lo;
-			if (!have && rank < avail) {
-				const unsigned i = chunk_lo + rank;
-				const int2 um = __ldcg(&F.ray_um[i]);
-				ffq = __ldcg(&F.ray_ff[i]);
-				u = um.x, row = um.y >> 1, half = um.y & 1;
-				const float4 v = __ldg(&S.uv[u]);
-				const ShooterRec *sr = F.rec + row;
-				const FFSample *smp = sr->splittable ? &sr->half[half] : &sr->centre;
-				logsrc = sr->logsrc;
-				px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
-				vx = smp->cx - px, vy = smp->cy - py, vz = smp->cz - pz;
-				qx = px, qy = py, qz = pz, prev = -1, guard = 0, steps = 0, t = 0.f;
-				have = 1;
-			}
-			chunk_lo += min((unsigned)__popc(idle), avail);
-			idle = __ballot_sync(0xffffffffu, !have);
+		if (i < 0) {
+			i = atomicAdd(&s_next, 1);
+			if (i >= total) break;
+			u = q_u[i], ffq = q_ff[i];
+			const float4 v = __ldg(&S.uv[u]);
+			px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
+			vx = smp.cx - px, vy = smp.cy - py, vz = smp.cz - pz;
+			qx = px, qy = py, qz = pz, prev = -1, guard = 0, steps = 0, t = 0.f;
 		}
-		if (!__any_sync(0xffffffffu, have)) break;
-		if (have) {
-			int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
-			const int cur = leaf_of<false>(T, qx, qy, qz, nullptr);
-			if (cur < 0 || ++steps > kMaxWalkSteps) {
-				verdict = 0;
-			} else if (prev == cur) {		// raycast.cpp:344-351
-				t = (float)((double)t + 1.0);
-				qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
-				if (++guard > 100000) verdict = 0;
+		int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
+		const int cur = leaf_of<false>(T, qx, qy, qz, nullptr);
+		if (cur < 0 || ++steps > kMaxWalkSteps) {
+			verdict = 0;
+		} else if (prev == cur) {		// raycast.cpp:344-351
+			t = (float)((double)t + 1.0);
+			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
+			if (++guard > 100000) verdict = 0;
+		} else {
+			const float4 lo = __ldg(&T.leaf_lo[cur]);
+			const float4 hi = __ldg(&T.leaf_hi[cur]);
+			if ((s_mask[cur >> 5] >> (cur & 31)) & 1u) {
+				int hit = -1;
+				float t_min = 1000000.0f;
+				const int *lp = T.list + __float_as_int(lo.w);
+				int idx;
+				while ((idx = __ldg(lp++)) >= 0) {
+					if (idx == ban) continue;
+					if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
+				}
+				if (hit >= 0) verdict = (hit == logsrc);
 			} else {
-				const float4 lo = __ldg(&T.leaf_lo[cur]);
-				const float4 hi = __ldg(&T.leaf_hi[cur]);
-				if ((__ldg(&F.row_mask[(size_t)row * F.mask_words + (cur >> 5)]) >> (cur & 31)) & 1u) {
-					int hit = -1;
-					float t_min = 1000000.0f;
-					const int *lp = T.list + __float_as_int(lo.w);
-					int idx;
-					while ((idx = __ldg(lp++)) >= 0) {
-						if (idx == ban) continue;
-						if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
-					}
-					if (hit >= 0) verdict = (hit == logsrc);
-				} else {
-					if (leaf_any_hit(T, __ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban)) verdict = 0;
-				}
-				if (verdict < 0) {	// NextPoint (raycast.cpp:235-251)
-					prev = cur;
-					float tn = 1000000.0f, s;
-					if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
-					if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
-					if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
-					tn = (float)((double)tn + 0.1);
-					qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
-					t = tn;
-				}
+				if (leaf_any_hit(T, __ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban)) verdict = 0;
 			}
-			if (verdict >= 0) {
-				float2 *out = F.ff + (size_t)row * S.U;
-				const float ff = verdict ? ffq : 0.0f;
-				if (half) out[u].y = ff; else out[u].x = ff;
-				have = 0;
+			if (verdict < 0) {	// NextPoint (raycast.cpp:235-251)
+				prev = cur;
+				float tn = 1000000.0f, s;
+				if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
+				if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
+				if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
+				tn = (float)((double)tn + 0.1);
+				qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
+				t = tn;
 			}
+		}
+		if (verdict >= 0) {
+			const float ff = verdict ? ffq : 0.0f;
+			if (half) out[u].y = ff; else out[u].x = ff;
+			i = -1;
 		}
 	}
 }
