@@ -70,7 +70,7 @@ struct radk_ctx {
 	std::vector<int> recv_parent;
 	std::vector<int> h_slot_to_recv;	// slot -> receiver index on this shard, -1 otherwise
 
-	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot, leaf_list4, tri_leaf_begin, tri_leaves;
+	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot, leaf_list4, tri_leaf_begin, tri_leaves, uv_leaf;
 	DevBuf<int4> list4;
 	DevBuf<unsigned> row_mask;
 	DevBuf<float4> leaf_lo, leaf_hi, occ, geo[3], st[3], st0[3], uv, par_n, par_fk;
@@ -345,6 +345,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(c->par_fk.upload(F.par_fk, st));
 	CUDA_TRY(c->vid.upload(F.vid, st));
 	CUDA_TRY(c->uv.upload(F.uv, st));
+	CUDA_TRY(c->uv_leaf.upload(F.uv_leaf, st));
 	CUDA_TRY(c->ffh.alloc(U));
 	CUDA_TRY(c->vstat.alloc(U));
 	CUDA_TRY(cudaMemsetAsync(c->ffh.p, 0, std::max(U, 1) * sizeof(float2), st));
@@ -445,7 +446,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	S.tree.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
 	S.R = R, S.U = U, S.n0 = s->n0;
 	for (int v = 0; v < 3; v++) S.geo[v] = c->geo[v].p, S.st[v] = c->st[v].p;
-	S.vid = c->vid.p, S.slot = c->slot.p, S.uv = c->uv.p, S.ffh = c->ffh.p, S.vstat = c->vstat.p;
+	S.vid = c->vid.p, S.slot = c->slot.p, S.uv = c->uv.p, S.uv_leaf = c->uv_leaf.p, S.ffh = c->ffh.p, S.vstat = c->vstat.p;
 	S.par_n = c->par_n.p, S.par_fk = c->par_fk.p, S.slot_to_recv = c->slot_to_recv.p;
 	S.converge = o.converge;
 	S.parallel_src = std::max(1, std::min(o.parallel_src, kMaxSources));

@@ -477,7 +477,9 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 			qx = px, qy = py, qz = pz, prev = -1, guard = 0, steps = 0, t = 0.f;
 		}
 		int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
-		const int cur = leaf_of<false>(T, qx, qy, qz, nullptr);
+		int cur;
+		if (steps == 0) cur = __ldg(&S.uv_leaf[u]);	// the first probe point is the vertex itself: its leaf is static
+		else cur = leaf_of<false>(T, qx, qy, qz, nullptr);
 		if (cur < 0 || ++steps > kMaxWalkSteps) {
 			verdict = 0;
 		} else if (prev == cur) {		// raycast.cpp:344-351

@@ -32,6 +32,7 @@ struct FlatScene {
 	std::vector<float4> par_n, par_fk;
 	std::vector<int4> vid;
 	std::vector<float4> uv;
+	std::vector<int> uv_leaf;	// leaf that contains the vertex = first leaf of every ray that starts there
 	std::string error;
 
 	DevTree host_tree(const radk_scene *s) const {	// the same view the kernels get, over host memory
@@ -267,6 +268,11 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 	std::sort(uorder.begin(), uorder.end(), [&](int a, int b) { return ukey2[a] != ukey2[b] ? ukey2[a] < ukey2[b] : a < b; });
 	F.uv.resize(U);
 	for (int i = 0; i < U; i++) unew[uorder[i]] = i, F.uv[i] = upos[uorder[i]];
+	{
+		const DevTree T = F.host_tree(s);
+		F.uv_leaf.resize(U);
+		for (int i = 0; i < U; i++) F.uv_leaf[i] = leaf_of<false>(T, F.uv[i].x, F.uv[i].y, F.uv[i].z, nullptr);
+	}
 	for (int r = 0; r < R; r++) F.vid[r] = i4(unew[F.vid[r].x], unew[F.vid[r].y], unew[F.vid[r].z], F.vid[r].w);
 	return RADK_OK;
 }

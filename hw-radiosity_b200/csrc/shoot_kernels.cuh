@@ -55,6 +55,7 @@ struct DevScene {
 	const int4 *vid;
 	const int *slot;		// [R] TriStore slot of receiver r (tie-break key, output order)
 	const float4 *uv;
+	const int *uv_leaf;		// [U] leaf containing the vertex (TreeNodeNum of the ray's first probe point, static)
 	float2 *ffh;			// [U] form factor toward half 0 / half 1 of the current shooter
 	unsigned *vstat;		// [U] statistics mode: packed sample counts
 	const float4 *par_n;		// [n0] n.xyz | norm(n)
