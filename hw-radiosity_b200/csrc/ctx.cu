@@ -245,6 +245,7 @@ int upload_split_scene(radk_ctx *c, const radk_scene *s) {
 	S.tree.nnodes = s->nnodes;
 	for (int k = 0; k < 3; k++) S.tree.G0[k] = s->G0[k], S.tree.G1[k] = s->G1[k];
 	S.tree.min_grid_len = s->min_grid_len, S.tree.grid_num = s->grid_num, S.tree.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
+	S.tree.inv_min_grid_len_f = (float)S.tree.inv_min_grid_len, S.tree.cell_eps = 4e-7f * (float)(s->grid_num + 1) + 1e-4f;
 	S.capacity = cap, S.limit = limit, S.trinum = c->sp_trinum.p;
 	for (int v = 0; v < 3; v++) S.p[v] = c->sp_p[v].p, S.st[v] = c->sp_st[v].p;
 	S.n = c->sp_n.p, S.fk = c->sp_fk.p, S.rec = c->sp_rec.p, S.count = c->sp_count.p, S.ffs = c->sp_ffs.p;
@@ -444,6 +445,8 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	S.tree.min_grid_len = s->min_grid_len;
 	S.tree.grid_num = s->grid_num;
 	S.tree.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
+	S.tree.inv_min_grid_len_f = (float)S.tree.inv_min_grid_len;
+	S.tree.cell_eps = 4e-7f * (float)(s->grid_num + 1) + 1e-4f;
 	S.R = R, S.U = U, S.n0 = s->n0;
 	for (int v = 0; v < 3; v++) S.geo[v] = c->geo[v].p, S.st[v] = c->st[v].p;
 	S.vid = c->vid.p, S.slot = c->slot.p, S.uv = c->uv.p, S.uv_leaf = c->uv_leaf.p, S.ffh = c->ffh.p, S.vstat = c->vstat.p;

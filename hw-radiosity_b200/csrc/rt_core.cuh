@@ -41,7 +41,9 @@ struct DevTree {
 	float G0[3], G1[3];
 	float min_grid_len;
 	int grid_num;
-	double inv_min_grid_len;	// 1.0 / (double)min_grid_len, see leaf_of
+	double inv_min_grid_len;	// 1.0 / (double)min_grid_len, see cell_index
+	float inv_min_grid_len_f;	// the same in float, and the guard band (in cells) within which the float
+	float cell_eps;			// estimate of a cell coordinate is not trusted (>= 0.25: never trusted)
 };
 // occluder record (the {n, c, se} of TriStore[idx] at shot time, raycast.cpp:288-309):
 //   q0 = n.x n.y n.z c.x | q1 = c.y c.z se00 se01 | q2 = se02 se03 se10 se11
@@ -87,8 +89,15 @@ RADK_HD float dot3(float ax, float ay, float az, float bx, float by, float bz) {
 // gnum = (int)(((double)q - G0) / MinGridLen) (raycast.cpp:263).  The double division is replaced by a
 // multiplication with the rounded reciprocal; both results differ from the exact quotient by less
 // than 1e-13, so their truncations can only disagree when the quotient lies within 1e-9 of an
-// integer - in that case the reference's division is evaluated instead.  Bit-identical by construction.
+// integer - in that case the reference's division is evaluated instead.  A float estimate with its own
+// (much wider) guard band is tried before any double-precision work.  Bit-identical by construction.
 RADK_HD int cell_index(const DevTree &T, float q, float g0) {
+	// float estimate first: its error is below cell_eps cells (three roundings of relative size 2^-24 on a
+	// value of at most grid_num + 1), so away from cell boundaries its truncation is the reference's
+	const float yf = (q - g0) * T.inv_min_grid_len_f;
+	const int nf = (int)yf;
+	const float ff = yf - (float)nf;
+	if (T.cell_eps < 0.25f && ff > T.cell_eps && ff < 1.0f - T.cell_eps) return nf;
 	const double x = (double)q - (double)g0;
 	const double y = x * T.inv_min_grid_len;
 	int n = (int)y;

@@ -45,6 +45,8 @@ struct FlatScene {
 		for (int k = 0; k < 3; k++) T.G0[k] = s->G0[k], T.G1[k] = s->G1[k];
 		T.min_grid_len = s->min_grid_len, T.grid_num = s->grid_num;
 		T.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
+		T.inv_min_grid_len_f = (float)T.inv_min_grid_len;
+		T.cell_eps = 4e-7f * (float)(s->grid_num + 1) + 1e-4f;
 		return T;
 	}
 };
