@@ -298,6 +298,11 @@ def run_ours(args):
         barrier()
 
     hbm_gbs, peak_src, sm_max = measured_peaks()
+    traffic = None                 # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     # dominant kernel: the visibility / form-factor kernel (K3a: ff_batch_kernel).  Algorithmic bytes per launch =
     # 160 B x shaded receivers of the shots whose form factors the launch produced.
     ff_ms, ff_n = kt["ms"]["form_factor"], max(kt["launches"]["form_factor"], 1)
@@ -329,7 +334,8 @@ def run_ours(args):
         "e2e": {"value": rays_per_step / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": state_bytes,
                 "d2h_bytes_per_step": state_bytes, "seconds_per_step": e2e_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": None, "kernel": dom, "peak_source": peak_src,
+                     "traffic": traffic, "kernel": dom, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo_bytes_per_step / ff_n,
                      "note": "achieved = 160 B x shaded receivers of the step / summed launch time of the dominant kernel "
                              "(CUDA events per launch, profiled run); church is FP32-issue/latency bound, not HBM bound "
                              "(SURVEY 8d): see fp32 and shot_roofline",
