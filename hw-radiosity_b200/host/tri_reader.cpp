@@ -3,7 +3,10 @@
 // normalised normal, area and the three inward side planes; scene cube G0/G1 from the bounds.
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <string>
+#include <vector>
 #include "model.hpp"
 
 namespace radk {
@@ -67,9 +70,51 @@ static void derive_geometry(radk_triangle &t) {
 	}
 }
 
+// .poly front end (the reference itself cannot read its model/*.poly files):
+// records "Fr Fg Fb Br Bg Bb N" followed by N vertex lines; an N-gon is fanned from its first vertex
+// (a b c d -> a b c, a c d), which is how the reference's sibling .tri files were made from the .poly ones.
+static bool poly_to_tri_text(const std::string &in, std::string &out) {
+	Cursor cur{in.c_str(), in.c_str() + in.size()};
+	char line[256];
+	for (;;) {
+		cur.skip_ws();
+		if (cur.s >= cur.end) break;
+		int col[6], n;
+		for (int k = 0; k < 6; k++)
+			if (!cur.integer(col[k])) return false;
+		if (!cur.integer(n) || n < 3 || n > 4096) return false;
+		std::vector<std::string> v((size_t)n);
+		for (int i = 0; i < n; i++) {		// vertex coordinates are passed through as text: no re-rounding
+			for (int k = 0; k < 3; k++) {
+				cur.skip_ws();
+				const char *b = cur.s;
+				float dummy;
+				if (!cur.real(dummy)) return false;
+				if (k) v[i] += ' ';
+				v[i].append(b, cur.s);
+			}
+		}
+		for (int i = 1; i + 1 < n; i++) {
+			snprintf(line, sizeof(line), "Triangle\n%d %d %d %d %d %d\n", col[0], col[1], col[2], col[3], col[4], col[5]);
+			out += line;
+			out += v[0] + "\n" + v[i] + "\n" + v[i + 1] + "\n";
+		}
+	}
+	return true;
+}
+
 int read_triangles(const char *text, size_t len, Model &m) {
 	// strtof/strtol need a terminated buffer
 	std::string owned(text, len);
+	{	// a .poly file starts with a number, a .tri file with the "Triangle" keyword
+		size_t i = 0;
+		while (i < owned.size() && (owned[i] == ' ' || owned[i] == '\t' || owned[i] == '\n' || owned[i] == '\r')) i++;
+		if (i < owned.size() && (owned[i] == '-' || owned[i] == '+' || (owned[i] >= '0' && owned[i] <= '9'))) {
+			std::string tri;
+			if (!poly_to_tri_text(owned, tri)) { set_error("malformed .poly input"); return RADK_ERR_IO; }
+			owned.swap(tri);
+		}
+	}
 	Cursor cur{owned.c_str(), owned.c_str() + owned.size()};
 	float lo[3] = {1000000.0f, 1000000.0f, 1000000.0f}, hi[3] = {-1000000.0f, -1000000.0f, -1000000.0f};
 	const int cap = m.opts.max_tri > 0 ? m.opts.max_tri : kRefMaxTri;

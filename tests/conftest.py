@@ -32,7 +32,7 @@ def models_dir(tmp_path_factory):
     d = tmp_path_factory.mktemp("models")
     src = os.path.join(GOLDEN_DIR, "models")
     for fn in os.listdir(src):
-        if fn.endswith(".tri.gz"):
+        if fn.endswith(".tri.gz") or fn.endswith(".poly.gz"):
             with gzip.open(os.path.join(src, fn)) as f, open(d / fn[:-3], "wb") as g:
                 g.write(f.read())
     return d

@@ -106,3 +106,18 @@ def test_colour_snapshot_writer_equals_plain_writer(hr, po, models_dir, tmp_path
         m.write_colors(str(tmp_path / "snap"), rgb, loop=loop)
         name = "snap.fin" if loop == 0 else f"snap.{loop}"
         assert (tmp_path / name).read_bytes() == want
+
+
+@pytest.mark.parametrize("name", ["box", "blocks", "model1"])
+def test_poly_input_equals_sibling_tri(hr, golden, models_dir, name):
+    """.poly front end (the reference ships .poly siblings it cannot read itself): fanning the N-gons gives
+    exactly the sibling .tri model, so the frozen mesh equals the reference's for that model."""
+    m = hr.Model(str(models_dir / f"{name}.poly"))
+    g = golden["models"][name]
+    assert (m.n0, m.trinum) == (g["n0"], g["trinum"])
+    assert sha(m.triangles) == g["tristore_sha"]
+
+
+def test_malformed_poly(hr):
+    with pytest.raises(hr.RadkError):
+        hr.Model(text=b"101 101 101 0 0 0 4\n0 0 0\n1 0 0\n")
