@@ -31,10 +31,10 @@ WORKLOADS = {
     "blocks": ("blocks", {}, {}, "model/blocks.tri frozen mesh, to convergence"),
     # seeded synthetic rooms (hw-radiosity_b200/synth.py), refined with the exhaustive PrePartition variant
     # -converge 1 keeps candidates alive for the fixed shot count (the small ceiling light alone would end after 2 shots)
-    "synth1m": ("synth:700000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {"converge": 1.0},
+    "synth1m": ("synth:700000", {"prepartition": 2, "tri_limit": 4000000, "max_tri": 4000000}, {"converge": 1.0},
                 "synthetic room, seed 1, ~1.4 M receivers, -converge 1, first 200 shots"),
-    "synth10m": ("synth:4800000", {"prepartition": 2, "tri_limit": 60000000, "max_tri": 60000000}, {"converge": 1.0},
-                 "synthetic room, seed 1, ~10 M receivers, -converge 1, fixed 1000 shots"),
+    "synth10m": ("synth:8100000", {"prepartition": 2, "tri_limit": 26000000, "max_tri": 26000000}, {"converge": 1.0},
+                 "synthetic room, seed 1, 11.6 M receivers, -converge 1, fixed 1000 shots"),
 }
 SHOT_CAP = {"room": 200, "box": 500, "synth1m": 200, "synth10m": 1000}
 ALGO_BYTES_PER_RECEIVER = 160
