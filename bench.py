@@ -298,6 +298,7 @@ def run_ours(args):
         barrier()
 
     hbm_gbs, peak_src, sm_max = measured_peaks()
+    hbm_gbs *= world               # aggregate peaks of the N GPUs the job runs on
     traffic = None                 # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
@@ -315,7 +316,7 @@ def run_ours(args):
     # FP32 side of the SURVEY section 8(d) roofline, counted per traced ray by the device itself
     flops = (35 * walk["calff"] + 12 * walk["leaf_visits"] + 6 * walk["descent_steps"] + 22 * (walk["leaf_visits"] - walk["tri_accepts"] * 0)
              + 14 * walk["tri_tests"] + 24 * walk["tri_accepts"])
-    p_fp32 = 148 * 128 * 2 * sm_max * 1e6
+    p_fp32 = 148 * 128 * 2 * sm_max * 1e6 * world
     line = {
         "metric": "visibility_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -334,7 +335,7 @@ def run_ours(args):
         "e2e": {"value": rays_per_step / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": state_bytes,
                 "d2h_bytes_per_step": state_bytes, "seconds_per_step": e2e_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": traffic, "kernel": dom, "peak_source": peak_src,
+                     "traffic": traffic, "kernel": dom, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                      "algorithmic_bytes_per_launch": algo_bytes_per_step / ff_n,
                      "note": "achieved = 160 B x shaded receivers of the step / summed launch time of the dominant kernel "
                              "(CUDA events per launch, profiled run); church is FP32-issue/latency bound, not HBM bound "
