@@ -560,6 +560,9 @@ void radk_ctx_destroy(radk_ctx *c) {
 		if (cudaMemcpy(t, c->dbg.p, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
 			fprintf(stderr, "[radk] predict phases (ns): scan+ticket %llu, top-K %llu, cache rebuild %llu, shooter records %llu, leaf masks %llu\n",
 				t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
+		if (cudaMemcpy(t, c->dbg.p, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[12])
+			fprintf(stderr, "[radk] shots_kernel CTA 0, ns per shot over %llu shots: update %llu, CTA reduce %llu, grid barrier %llu, scan + next shooter %llu\n",
+				t[12], t[8] / t[12], t[9] / t[12], t[10] / t[12], t[11] / t[12]);
 	}
 	if (c->h_flags) cudaFreeHost(c->h_flags);
 	if (c->h_shots) cudaFreeHost(c->h_shots);

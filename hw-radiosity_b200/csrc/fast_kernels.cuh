@@ -604,9 +604,13 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 	int parity = 0;
 	long long done = 0;
 	int stalled = 0;
+	unsigned long long tA = 0, tB = 0, tC = 0, tD = 0, tmark = 0;
+	const bool dbg = F.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+	auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
 	while (true) {
 		if (!cur.valid || budget <= 0) break;
 		if (cur.row < 0) { stalled = 1; break; }
+		if (dbg) tmark = now();
 		const float2 *ffrow = F.ff + (size_t)cur.row * S.U;
 		const int shooter_slot = cur.slot;
 		const float sdB0 = cur.dB[0], sdB1 = cur.dB[1], sdB2 = cur.dB[2];
@@ -639,6 +643,7 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 				if (kk > key) key = kk, kd0 = a0.w, kd1 = a1.w, kd2 = a2.w;
 			}
 		}
+		if (dbg) { const unsigned long long t = now(); tA += t - tmark; tmark = t; }
 		// CTA argmax carrying the winner's unshot energy
 		const unsigned long long wmax = warp_max_u64(key);
 		const unsigned src = __ffs(__ballot_sync(0xffffffffu, key == wmax && wmax != 0ull)) - 1;
@@ -666,7 +671,9 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			// 128-bit loads, and the winner's cache row is looked up in the shared-memory directory, so the
 			// barrier is followed by a single L2 round trip.
 			if (threadIdx.x == 0) F.partial[parity * max_ctas + blockIdx.x] = s_best;
+			if (dbg) { const unsigned long long t = now(); tB += t - tmark; tmark = t; }
 			grid_barrier(F.barrier, epoch * (unsigned)nctas);
+			if (dbg) { const unsigned long long t = now(); tC += t - tmark; tmark = t; }
 			unsigned long long k = 0ull;
 			float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 			if (threadIdx.x < nctas) {
@@ -763,6 +770,7 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			cur = n;
 		}
 		__syncthreads();
+		if (dbg) { const unsigned long long t = now(); tD += t - tmark; tmark = t; }
 		done++, budget--, parity ^= 1;
 	}
 	if (RPT > 0) {	// write the resident state back
@@ -772,6 +780,7 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			if (rslot[k] >= 0) S.st[0][r] = ra0[k], S.st[1][r] = ra1[k], S.st[2][r] = ra2[k];
 		}
 	}
+	if (dbg) { F.dbg[8] += tA, F.dbg[9] += tB, F.dbg[10] += tC, F.dbg[11] += tD, F.dbg[12] += (unsigned long long)done; }
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		*F.handoff = cur;
 		*F.budget = budget;
