@@ -9,6 +9,7 @@
 //   -gpu <n>        CUDA device ordinal (default 0)
 //   -max_tri <n>    raise the reference's compile-time MaxTri pool limit (rad.h:9)
 //   -stats          print device ray statistics at the end
+//   -gpus <n>       shard the receivers over n GPUs of this box (devices gpu .. gpu+n-1), one host thread each
 //   -split          adaptive splitting inside the loop on the device (the reference's split-enabled build:
 //                   config.h without DONT_PARTITION/PRE_PARTITION); -adapt_area/-sample_area/-delta_ff then act
 #include <chrono>
@@ -16,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "radk.h"
@@ -33,7 +35,7 @@ struct Options {
 	int triangle = 1000000;
 	float light = 1.0f;
 	int write_cycle = 10, zip = 0, interactive = 0, jobs = 2, parallel_src = 1;
-	int gpu = 0, max_tri = 0, stats = 0, split = 0;
+	int gpu = 0, gpus = 1, max_tri = 0, stats = 0, split = 0;
 	const char *input = nullptr;
 	const char *prefix = "./test";
 };
@@ -79,6 +81,7 @@ void usage(const char *argv0, const Options &d) {
 	fprintf(stderr, "                               " KMAG "Defulat false\n" KWHT);
 	fprintf(stderr, "   Device Options (this implementation)\n");
 	fprintf(stderr, "       -gpu <integer>          CUDA device ordinal.  -max_tri <integer>  triangle pool size.  -stats\n");
+	fprintf(stderr, "       -gpus <integer>         Shard the receivers over this many GPUs.\n");
 	fprintf(stderr, "       -split                  Adaptive splitting inside the loop (reference built without DONT_PARTITION).\n");
 }
 
@@ -120,6 +123,7 @@ bool process_options(int argc, char **argv, Options &o) {
 		else if (a == "-jobs") ok = want_int(argc, argv, i, o.jobs, "Parallel Jobs");
 		else if (a == "-parallel_src") ok = want_int(argc, argv, i, o.parallel_src, "Parallel Source");
 		else if (a == "-gpu") ok = want_int(argc, argv, i, o.gpu, "GPU");
+		else if (a == "-gpus") ok = want_int(argc, argv, i, o.gpus, "GPUs");
 		else if (a == "-max_tri") ok = want_int(argc, argv, i, o.max_tri, "MaxTri");
 		else if (a == "-stats") o.stats = 1;
 		else if (a == "-split") o.split = 1;
@@ -146,7 +150,8 @@ void after_write(const Options &o, const std::string &fn) {
 	}
 }
 
-bool write_snapshot(radk_ctx *ctx, radk_model *model, const Options &o, int loop) {
+bool write_snapshot(const std::vector<radk_ctx *> &ctxs, radk_model *model, const Options &o, int loop) {
+	radk_ctx *ctx = ctxs[0];
 	if (o.split) {		// the pool grew on the device: fetch whole records
 		int n = 0;
 		radk_ctx_download_triangles(ctx, nullptr, 0, &n);
@@ -167,6 +172,18 @@ bool write_snapshot(radk_ctx *ctx, radk_model *model, const Options &o, int loop
 	if (radk_ctx_snapshot_colors(ctx, rgb.data(), trinum) != RADK_OK) {
 		fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
 		return false;
+	}
+	if (ctxs.size() > 1) {		// every rank reports its own receivers (-1 elsewhere): merge the shards
+		static std::vector<int> part;
+		part.resize(rgb.size());
+		for (size_t r = 1; r < ctxs.size(); r++) {
+			if (radk_ctx_snapshot_colors(ctxs[r], part.data(), trinum) != RADK_OK) {
+				fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
+				return false;
+			}
+			for (size_t k = 0; k < rgb.size(); k++)
+				if (part[k] >= 0) rgb[k] = part[k];
+		}
 	}
 	radk_model_write_colors(model, o.prefix, loop, rgb.data(), trinum);
 	if (o.zip || o.interactive || loop == 0) {
@@ -236,11 +253,35 @@ int main(int argc, char **argv) {
 	co.area_limit = o.adapt_area, co.sample_area = radk_model_sample_area(model), co.delta_ff = o.delta_ff;
 	co.device = o.gpu, co.collect_stats = o.stats, co.split_enabled = o.split;
 	if (o.max_tri > 0) co.max_tri = o.max_tri;
-	radk_ctx *ctx = nullptr;
-	if (radk_ctx_create(&sc, &co, &ctx) != RADK_OK) {
-		fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
-		return 1;
+	const int ngpu = (o.gpus > 1 && !o.split && !o.stats && o.parallel_src <= 1) ? o.gpus : 1;
+	std::vector<radk_ctx *> ctxs((size_t)ngpu, nullptr);
+	for (int r = 0; r < ngpu; r++) {
+		co.device = o.gpu + r, co.rank = r, co.world = ngpu;
+		if (radk_ctx_create(&sc, &co, &ctxs[r]) != RADK_OK) {
+			fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
+			return 1;
+		}
 	}
+	for (int r = 0; r < ngpu && ngpu > 1; r++)
+		if (radk_ctx_peer_connect_local(ctxs[r], ctxs.data(), ngpu) != RADK_OK) {
+			fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
+			return 1;
+		}
+	radk_ctx *ctx = ctxs[0];
+	// all ranks step together (each blocks on its own stream while exchanging candidates with its peers)
+	auto step_all = [&](long long chunk, long long *done, int *converged) {
+		if (ngpu == 1) return radk_ctx_step(ctx, chunk, done, converged);
+		std::vector<int> rc((size_t)ngpu, RADK_OK);
+		std::vector<long long> d((size_t)ngpu, 0);
+		std::vector<int> cv((size_t)ngpu, 0);
+		std::vector<std::thread> th;
+		for (int r = 0; r < ngpu; r++) th.emplace_back([&, r] { rc[r] = radk_ctx_step(ctxs[r], chunk, &d[r], &cv[r]); });
+		for (auto &t : th) t.join();
+		for (int r = 0; r < ngpu; r++)
+			if (rc[r] != RADK_OK) return rc[r];
+		*done = d[0], *converged = cv[0];
+		return (int)RADK_OK;
+	};
 
 	// DoRadiosity's loop (rad.cpp:497-516): iteration `loop` is shot number `loop`; a snapshot is
 	// written after every write_cycle-th shot; the iteration that finds no shooter ends the loop.
@@ -250,7 +291,7 @@ int main(int argc, char **argv) {
 		const long long chunk = W - shots % W;
 		long long done = 0;
 		int converged = 0;
-		if (radk_ctx_step(ctx, chunk, &done, &converged) != RADK_OK) {
+		if (step_all(chunk, &done, &converged) != RADK_OK) {
 			fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
 			return 1;
 		}
@@ -261,13 +302,13 @@ int main(int argc, char **argv) {
 		}
 		if (shots % W == 0) {
 			fprintf(stderr, "[" KGRN "INFO" KWHT "] Loop %lld BEGIN\n", shots);
-			write_snapshot(ctx, model, o, (int)shots);
+			write_snapshot(ctxs, model, o, (int)shots);
 			fprintf(stderr, "[" KGRN "INFO" KWHT "] END Loop. There are %i triangles.\n", radk_ctx_trinum(ctx));
 		}
 	}
 	fprintf(stderr, "[" KGRN "INFO" KWHT "] Complete in #Iterations %lld\n", shots + 1);
 	double w0 = now();
-	write_snapshot(ctx, model, o, 0);
+	write_snapshot(ctxs, model, o, 0);
 	double w1 = now();
 	fprintf(stderr, "[" KGRN "INFO" KWHT "] Store file took " KMAG "%f" KWHT " sec. time.\n", w1 - w0);
 	if (o.stats) {
@@ -277,7 +318,7 @@ int main(int argc, char **argv) {
 				"%.3f ms in the loop, %lld kernel launches\n", st.shots, st.rays, st.visible, st.traced_rays,
 				radk_ctx_device_ms(ctx), st.kernel_launches);
 	}
-	radk_ctx_destroy(ctx);
+	for (radk_ctx *c : ctxs) radk_ctx_destroy(c);
 	radk_model_free(model);
 	fprintf(stderr, "[" KGRN "INFO" KWHT "] Radiosity Method took " KMAG "%f" KWHT " sec. time.\n", now() - r0);
 	return 0;

@@ -72,3 +72,16 @@ def test_split_switch_matches_split_enabled_reference(models_dir, golden, tmp_pa
     assert re.findall(rb"Complete in #Iterations (\d+)", r.stderr) == [str(g["shots"] + 1).encode()]
     text = (tmp_path / "s.fin").read_bytes()
     assert text.count(b"Triangle \n") == g["leaves"]
+
+
+@pytest.mark.gpu
+def test_multi_gpu_switch(models_dir, golden, tmp_path):
+    """`rad -gpus N`: receiver shards on N devices of the box, one host thread each; same .fin bytes."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = run(RAD, ["-gpus", str(n), "-write_cycle", "100", str(models_dir / "sbox.tri"), "-o", "m"], tmp_path)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")
+    assert hashlib.sha256((tmp_path / "m.fin").read_bytes()).hexdigest() == golden["models"]["sbox"]["full"]["fin_sha"]
+    assert sorted(os.listdir(tmp_path)) == ["m.100", "m.200", "m.300", "m.400", "m.500", "m.fin"]
