@@ -274,16 +274,25 @@ def run_ours(args):
         # end-to-end through the C ABI with host buffers: state upload + loop + download
         host_out = ctx.download()            # caller-owned host buffers, reused every step
 
+        phases = [0.0, 0.0, 0.0]
+
         def e2e_step():
             barrier()
             t = time.perf_counter()
             ctx.reset(model)                 # H2D: accB/deltaB of this rank's receivers from the host TriStore image
+            t1 = time.perf_counter()
             ctx.step(cap)
+            t2 = time.perf_counter()
             ctx.download(out=host_out)       # D2H: accB/deltaB of this rank's receivers into the host buffers
-            return max_over_ranks(time.perf_counter() - t)
+            t3 = time.perf_counter()
+            for k, d in enumerate((t1 - t, t2 - t1, t3 - t2)):
+                phases[k] += d
+            return max_over_ranks(t3 - t)
         for _ in range(2):
             e2e_step()
+        phases[:] = [0.0, 0.0, 0.0]
         e2e_s = sum(e2e_step() for _ in range(args.steps)) / args.steps
+        e2e_phases = {k: round(v / args.steps * 1e3, 3) for k, v in zip(("upload_ms", "loop_ms", "download_ms"), phases)}
         state_bytes = sizes["receivers"] * 48
 
         # CPU baseline on this box's host cores (rank 0, N=1 only): the unmodified reference, bounded sample
@@ -333,7 +342,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "e2e": {"value": rays_per_step / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": state_bytes,
-                "d2h_bytes_per_step": state_bytes, "seconds_per_step": e2e_s},
+                "d2h_bytes_per_step": state_bytes, "seconds_per_step": e2e_s, **e2e_phases},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": traffic, "kernel": dom, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                      "algorithmic_bytes_per_launch": algo_bytes_per_step / ff_n,

@@ -8,7 +8,11 @@
 #include <cstring>
 #include <cstdlib>
 #include <numeric>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -61,6 +65,7 @@ struct radk_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};	// kStageChunks
 	double device_ms = 0;
 	long long launches = 0;
 
@@ -126,6 +131,68 @@ namespace {
 
 const int kShotLogCap = 1 << 20;
 const int kBatchShots = 32;
+
+// Host-side gather / scatter between the caller's TriStore-shaped buffers and the pinned staging planes is a
+// strided walk over hundreds of MB on large scenes: a small persistent pool of host threads shares it
+// (RADK_HOST_THREADS, default min(8, cores); small jobs stay on the calling thread).
+class HostPool {
+public:
+	static HostPool &get() { static HostPool p; return p; }
+	template <typename F> void run(size_t n, F fn) {
+		const int nt = (int)std::min<size_t>((size_t)workers_.size() + 1, n / 8192 + 1);
+		if (nt <= 1) { fn((size_t)0, n); return; }
+		std::lock_guard<std::mutex> one_caller(run_m_);	// contexts driven from different host threads take turns
+		const size_t chunk = (n + nt - 1) / nt;
+		std::function<void(int)> job = [&](int k) { fn(std::min(n, k * chunk), std::min(n, (k + 1) * chunk)); };
+		{
+			std::lock_guard<std::mutex> g(m_);
+			job_ = &job, parts_ = nt, next_ = 1, pending_ = nt - 1, gen_++;
+		}
+		cv_.notify_all();
+		job(0);
+		std::unique_lock<std::mutex> g(m_);
+		done_.wait(g, [&] { return pending_ == 0; });
+		job_ = nullptr;
+	}
+private:
+	HostPool() {
+		const char *e = getenv("RADK_HOST_THREADS");
+		int t = e ? atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+		t = std::max(1, std::min(t, 64));
+		for (int k = 1; k < t; k++) workers_.emplace_back([this] { loop(); });
+	}
+	~HostPool() {
+		{ std::lock_guard<std::mutex> g(m_); stop_ = true; }
+		cv_.notify_all();
+		for (auto &t : workers_) t.join();
+	}
+	void loop() {
+		unsigned long long seen = 0;
+		std::unique_lock<std::mutex> g(m_);
+		for (;;) {
+			cv_.wait(g, [&] { return stop_ || (gen_ != seen && job_ && next_ < parts_); });
+			if (stop_) return;
+			while (job_ && next_ < parts_) {
+				const int k = next_++;
+				std::function<void(int)> *job = job_;
+				g.unlock();
+				(*job)(k);
+				g.lock();
+				if (--pending_ == 0) done_.notify_all();
+			}
+			seen = gen_;
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex m_, run_m_;
+	std::condition_variable cv_, done_;
+	std::function<void(int)> *job_ = nullptr;
+	int parts_ = 0, next_ = 0, pending_ = 0;
+	unsigned long long gen_ = 0;
+	bool stop_ = false;
+};
+template <typename F> void host_parallel_for(size_t n, F fn) { HostPool::get().run(n, fn); }
+constexpr int kStageChunks = 4;	// upload / download are pipelined in this many receiver ranges
 
 int reset_fast_state(radk_ctx *c) {
 	if (!c->use_fast) return RADK_OK;
@@ -567,6 +634,7 @@ void radk_ctx_destroy(radk_ctx *c) {
 	if (c->h_flags) cudaFreeHost(c->h_flags);
 	if (c->h_shots) cudaFreeHost(c->h_shots);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
+	for (auto e : c->stage_ev) if (e) cudaEventDestroy(e);
 	if (c->h_budget) cudaFreeHost(c->h_budget);
 	if (c->h_error) cudaFreeHost(c->h_error);
 	for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
@@ -583,14 +651,22 @@ int radk_ctx_reset(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(cudaSetDevice(c->device));
 	if (!c->h_stage) CUDA_TRY(cudaMallocHost((void **)&c->h_stage, 3 * (size_t)std::max(c->R, 1) * sizeof(float4)));
 	const size_t R = (size_t)c->R;
-	for (size_t r = 0; r < R; r++) {	// gather from the caller's TriStore image into pinned planes
-		const radk_triangle &t = s->tri[c->recv_slot[r]];
-		for (int v = 0; v < 3; v++) c->h_stage[v * R + r] = make_float4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
+	// gather from the caller's TriStore image into pinned planes, one receiver range at a time: the copy of a
+	// range is in flight while the next one is gathered
+	for (int k = 0; k < kStageChunks; k++) {
+		const size_t b = R * k / kStageChunks, e = R * (k + 1) / kStageChunks;
+		if (e == b) continue;
+		host_parallel_for(e - b, [=](size_t r0, size_t r1) {
+			for (size_t r = b + r0; r < b + r1; r++) {
+				const radk_triangle &t = s->tri[c->recv_slot[r]];
+				for (int v = 0; v < 3; v++) c->h_stage[v * R + r] = make_float4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
+			}
+		});
+		for (int v = 0; v < 3; v++)
+			CUDA_TRY(cudaMemcpyAsync(c->st[v].p + b, c->h_stage + v * R + b, (e - b) * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
 	}
-	for (int v = 0; v < 3; v++) {
-		CUDA_TRY(cudaMemcpyAsync(c->st[v].p, c->h_stage + v * R, R * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	for (int v = 0; v < 3; v++)
 		CUDA_TRY(cudaMemcpyAsync(c->st0[v].p, c->st[v].p, R * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
-	}
 	CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->shots_done.p, 0, sizeof(long long), c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->stats.p, 0, sizeof(DevStats), c->stream));
@@ -825,18 +901,32 @@ int radk_ctx_download(radk_ctx *c, float *accB, float *deltaB, int *parent, int 
 	}
 	if (!c->h_stage) CUDA_TRY(cudaMallocHost((void **)&c->h_stage, 3 * (size_t)std::max(c->R, 1) * sizeof(float4)));
 	const size_t R = (size_t)c->R;
-	for (int v = 0; v < 3; v++)
-		CUDA_TRY(cudaMemcpyAsync(c->h_stage + v * R, c->st[v].p, R * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	for (size_t r = 0; r < R; r++) {
-		const size_t slot = (size_t)c->recv_slot[r];
-		const float4 a0 = c->h_stage[r], a1 = c->h_stage[R + r], a2 = c->h_stage[2 * R + r];
-		if (accB) {
-			float *a = accB + slot * 9;
-			a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a1.x, a[4] = a1.y, a[5] = a1.z, a[6] = a2.x, a[7] = a2.y, a[8] = a2.z;
-		}
-		if (deltaB) deltaB[slot * 3] = a0.w, deltaB[slot * 3 + 1] = a1.w, deltaB[slot * 3 + 2] = a2.w;
-		if (parent) parent[slot] = c->recv_parent[r];
+	// one receiver range at a time: a range is scattered into the caller's slot-indexed buffers while the
+	// copies of the following ranges are still in flight
+	if (!c->stage_ev[0])
+		for (auto &e : c->stage_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	for (int k = 0; k < kStageChunks; k++) {
+		const size_t b = R * k / kStageChunks, e = R * (k + 1) / kStageChunks;
+		for (int v = 0; v < 3 && e > b; v++)
+			CUDA_TRY(cudaMemcpyAsync(c->h_stage + v * R + b, c->st[v].p + b, (e - b) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaEventRecord(c->stage_ev[k], c->stream));
+	}
+	for (int k = 0; k < kStageChunks; k++) {
+		const size_t b = R * k / kStageChunks, e = R * (k + 1) / kStageChunks;
+		CUDA_TRY(cudaEventSynchronize(c->stage_ev[k]));
+		if (e == b) continue;
+		host_parallel_for(e - b, [=](size_t r0, size_t r1) {
+			for (size_t r = b + r0; r < b + r1; r++) {
+				const size_t slot = (size_t)c->recv_slot[r];
+				const float4 a0 = c->h_stage[r], a1 = c->h_stage[R + r], a2 = c->h_stage[2 * R + r];
+				if (accB) {
+					float *a = accB + slot * 9;
+					a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a1.x, a[4] = a1.y, a[5] = a1.z, a[6] = a2.x, a[7] = a2.y, a[8] = a2.z;
+				}
+				if (deltaB) deltaB[slot * 3] = a0.w, deltaB[slot * 3 + 1] = a1.w, deltaB[slot * 3 + 2] = a2.w;
+				if (parent) parent[slot] = c->recv_parent[r];
+			}
+		});
 	}
 	return RADK_OK;
 }
