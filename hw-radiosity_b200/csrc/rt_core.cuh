@@ -254,6 +254,130 @@ RADK_HD bool leaf_any_hit(const DevTree &T, int list4_off, float px, float py, f
 	}
 }
 
+// ---- bounded any-hit: one code path for leaves with and without the shooter's original ----------------
+// TriListHitted (raycast.cpp:316-333) returns the accepted entry with the smallest t, the earliest list
+// position (= smallest index, the lists are ascending) winning ties, because a later entry with
+// t >= t_min is rejected.  With Acc = {entries that pass t > 0.0001, t < 1e6 and the inside test} the
+// shooter's original `logsrc` is returned iff logsrc is in Acc and no other e in Acc has
+// t_e < t_src or (t_e == t_src and e < logsrc).  So a leaf that lists logsrc is handled as: test logsrc
+// alone (against 1e6), then scan the list for ANY entry accepted under the bound (t_max, tie) =
+// (t_src, logsrc); a leaf that does not list it is the same scan with the bound (1e6, -1), which is
+// the plain "t >= 1e6 -> reject".  Both kinds of leaves therefore run the same instructions and the
+// scan stops at the first blocker.  The reference's behaviour once a NaN t (0/0) has been accepted is
+// order dependent (every later comparison with t_min is false); such a visit returns 2 and the caller
+// falls back to the sequential scan.
+RADK_HD int any_hit_bounded_one(const DevTree &T, int entry, float px, float py, float pz, float vx, float vy, float vz,
+				int ban, float t_max, int tie) {
+	const int idx = entry & kIdMask;
+	if (idx == ban) return 0;
+	const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
+	const float4 q0 = ldg(o), q1 = ldg(o + 1);
+	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
+	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
+	if ((a1 > 0.0f && a2 <= 0.0f) || (a1 < 0.0f && a2 >= 0.0f)) return 0;	// t <= 0: certain rejection
+	const float t = a2 / a1;
+	if (t <= 0.0001f) return 0;
+	if (t > t_max || (t == t_max && idx >= tie)) return 0;
+	if (!(entry & kPlaneFlag)) {	// zero side planes: the inside test cannot fail
+		const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
+		const float4 q2 = ldg(o + 2);
+		if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) return 0;
+		const float4 q3 = ldg(o + 3);
+		if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) return 0;
+		const float4 q4 = ldg(o + 4);
+		if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) return 0;
+	}
+	return t != t ? 2 : 1;
+}
+
+// 0: nothing accepted under the bound, 1: some entry accepted (blocker), 2: an accepted entry has a NaN t
+RADK_HD int leaf_any_hit_bounded(const DevTree &T, int list4_off, float px, float py, float pz, float vx, float vy, float vz,
+				 int ban, float t_max, int tie) {
+	const int4 *l4 = T.list4 + list4_off;
+	for (;;) {
+		const int4 id = ldg(l4++);
+		int r;
+		if (id.x < 0) return 0;
+		if ((r = any_hit_bounded_one(T, id.x, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
+		if (id.y < 0) return 0;
+		if ((r = any_hit_bounded_one(T, id.y, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
+		if (id.z < 0) return 0;
+		if ((r = any_hit_bounded_one(T, id.z, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
+		if (id.w < 0) return 0;
+		if ((r = any_hit_bounded_one(T, id.w, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
+	}
+}
+
+// The exact sequential scan (TriListHitted, raycast.cpp:316-333) compared with logsrc; only reached when a
+// NaN t was accepted in a leaf that lists logsrc, so it is kept out of line (registers of the hot path).
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+int leaf_visit_exact(const int *lp, const float4 *occ, float px, float py, float pz, float vx, float vy, float vz, int ban, int logsrc) {
+	int hit = -1;
+	float t_min = 1000000.0f;
+	int idx;
+	while ((idx = ldg(lp++)) >= 0) {
+		if (idx == ban) continue;
+		if (tri_hit(occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
+	}
+	return hit < 0 ? -1 : (hit == logsrc);
+}
+
+// One leaf visit of a shooter-visibility ray: -1 nothing hit here (walk on), 0 the walk ends on another
+// triangle, 1 the walk ends on logsrc.  Same answer as TriListHitted(...) compared with logsrc.
+RADK_HD int leaf_visit(const DevTree &T, int cur, bool lists_src, float px, float py, float pz, float vx, float vy, float vz,
+		       int ban, int logsrc) {
+	float t_max = 1000000.0f;
+	int tie = -1;
+	bool src_hit = false;
+	if (lists_src && logsrc != ban) {
+		src_hit = tri_hit(T.occ + (size_t)logsrc * OCC_STRIDE, px, py, pz, vx, vy, vz, t_max);
+		if (src_hit) tie = logsrc;
+	}
+	int r = (t_max != t_max) ? 2 : leaf_any_hit_bounded(T, ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban, t_max, tie);
+	if (r == 2) {
+		if (!lists_src) return 0;	// without logsrc in the list any acceptance ends the walk elsewhere
+		return leaf_visit_exact(T.list + float_as_int_hd(ldg(&T.leaf_lo[cur]).w), T.occ, px, py, pz, vx, vy, vz, ban, logsrc);
+	}
+	if (r == 1) return 0;
+	return src_hit ? 1 : -1;
+}
+
+// ray_sees with leaf_visit (the walk of ff_stream_kernel)
+template <typename MaskPtr>
+RADK_HD bool ray_sees_bounded(const DevTree &T, MaskPtr has_src, float px, float py, float pz, float vx, float vy, float vz,
+			      int ban, int logsrc) {
+	float t = 0.f;
+	int prev = -1, cur;
+	float qx = px, qy = py, qz = pz;
+	int guard = 0, steps = 0;
+	while ((cur = leaf_of<false>(T, qx, qy, qz, nullptr)) >= 0) {
+		if (++steps > kMaxWalkSteps) return false;
+		if (prev == cur) {		// raycast.cpp:344-351
+			t = (float)((double)t + 1.0);
+			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
+			if (++guard > 100000) return false;
+			continue;
+		}
+		const int v = leaf_visit(T, cur, (has_src[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
+		if (v >= 0) return v == 1;
+		const float4 lo = ldg(&T.leaf_lo[cur]);
+		const float4 hi = ldg(&T.leaf_hi[cur]);
+		prev = cur;
+		float tn = 1000000.0f, s;
+		if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
+		if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
+		if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
+		tn = (float)((double)tn + 0.1);
+		qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
+		t = tn;
+	}
+	return false;
+}
+
 template <typename MaskPtr>
 RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, float pz, float vx, float vy, float vz,
 		      int ban, int logsrc) {
