@@ -21,7 +21,6 @@
 #include "radk.h"
 #include "shoot_kernels.cuh"
 #include "fast_kernels.cuh"
-#include "ff_stream_kernel.cuh"
 #include "split_kernels.cuh"
 #include "scene_flatten.hpp"
 
@@ -108,9 +107,6 @@ struct radk_ctx {
 	FastState F{};
 	bool use_fast = false;
 	int rows = 0, shots_ctas = 0, shots_rpt = 0;
-	bool ff_batch_phased = false;
-	const void *ff_stream_fn = nullptr;
-	int ff_stream_ctas = 0;		// persistent grid of ff_stream_kernel; 0: RADK_FF_KERNEL=batch selected ff_batch_kernel
 	const void *shots_fn = nullptr;
 	long long *h_budget = nullptr;		// pinned
 	int max_blocks = 0;
@@ -219,19 +215,13 @@ int reset_fast_state(radk_ctx *c) {
 // ev (optional): 4 events recorded around the three kernels, for profiling.
 int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	cudaStream_t st = c->stream;
-	CUDA_TRY(cudaMemsetAsync(c->F.barrier, 0, 2 * sizeof(unsigned), st));	// barrier + ff_work
+	CUDA_TRY(cudaMemsetAsync(c->F.barrier, 0, sizeof(unsigned), st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
 	predict_kernel<<<64, 1024, 0, st>>>(c->S, c->F);
 	if (c->F.world > 1) { predict_merge_kernel<<<1, 256, 0, st>>>(c->S, c->F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-	if (c->ff_stream_ctas > 0) {
-		void *fargs[] = {(void *)&c->S, (void *)&c->F};
-		CUDA_TRY(cudaLaunchKernel(c->ff_stream_fn, dim3((unsigned)c->ff_stream_ctas), dim3(kFSBlock), fargs, 0, st));
-	} else {
-		const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
-		if (c->ff_batch_phased) ff_batch_kernel<true><<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
-		else ff_batch_kernel<false><<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
-	}
+	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
+	ff_batch_kernel<<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	int max_ctas = c->shots_ctas;
 	void *args[] = {(void *)&c->S, (void *)&c->F, (void *)&max_ctas};
@@ -469,23 +459,6 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 			break;
 		}
 		if (c->shots_rpt < 0) { set_error("shots_kernel does not fit this device"); return RADK_ERR_CUDA; }
-		{	// form-factor kernel: persistent streaming grid unless RADK_FF_KERNEL=batch asks for the tiled one
-			const char *e = getenv("RADK_FF_KERNEL");
-			c->ff_stream_ctas = 0;
-			c->ff_batch_phased = e && !strcmp(e, "phased");
-			if (!e || (strcmp(e, "batch") != 0 && strcmp(e, "phased") != 0)) {
-				int per_sm = 0;
-				c->ff_stream_fn = (const void *)ff_stream_kernel<5, 1>;
-				if (e && !strcmp(e, "s42")) c->ff_stream_fn = (const void *)ff_stream_kernel<4, 2>;
-				if (e && !strcmp(e, "s52")) c->ff_stream_fn = (const void *)ff_stream_kernel<5, 2>;
-				if (e && !strcmp(e, "s41")) c->ff_stream_fn = (const void *)ff_stream_kernel<4, 1>;
-				CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->ff_stream_fn, kFSBlock, 0));
-				if (per_sm < 1) { set_error("ff_stream_kernel does not fit this device"); return RADK_ERR_CUDA; }
-				const long long tiles = (U + kFSTile - 1) / kFSTile;
-				const long long chunks = (long long)rows * 2 * ((tiles + kFSChunk - 1) / kFSChunk);
-				c->ff_stream_ctas = (int)std::max<long long>(1, std::min<long long>((long long)dev_sms * per_sm, chunks));
-			}
-		}
 		CUDA_TRY(c->ffcache.alloc((size_t)rows * std::max(U, 1)));
 		CUDA_TRY(c->row_slot.alloc(kMaxRows));
 		CUDA_TRY(c->slot_row.alloc(std::max(s->trinum, 1)));
@@ -506,7 +479,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		FastState &F = c->F;
 		F.ff = c->ffcache.p, F.rows = rows, F.row_slot = c->row_slot.p, F.slot_row = c->slot_row.p;
 		F.rec = c->row_rec.p, F.todo = c->todo.p, F.ntodo = c->fast_ints.p, F.stalled = c->fast_ints.p + 1;
-		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.barrier = c->fast_uints.p + 1, F.ff_work = c->fast_uints.p + 2;
+		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.barrier = c->fast_uints.p + 1;
 		F.handoff = c->handoff.p, F.partial = c->partial.p, F.budget = c->budget.p;
 		F.row_mask = c->row_mask.p, F.mask_words = mask_words;
 		for (int t = 0; t < kMaxWorld; t++) F.box[t] = nullptr;

@@ -101,7 +101,6 @@ struct FastState {
 	ShotRec *handoff;		// current shooter between kernels
 	Partial *partial;		// [2][max CTAs], 32-byte records
 	unsigned *barrier;		// grid barrier counter (zeroed before each shots launch)
-	unsigned *ff_work;		// next work unit of ff_stream_kernel (zeroed with the barrier counter)
 	long long *budget;		// shots the current radk_ctx_step call may still run
 	unsigned *row_mask;		// [rows][mask_words] bit n set <=> leaf n's list contains the row's logsrc
 	int mask_words;
@@ -399,9 +398,9 @@ __global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastStat
 
 // ---- batched form factors -----------------------------------------------------------------------
 constexpr int kFFBlock = 256;
-constexpr int kFFItems = 4;	// candidate vertices per thread before compaction
+constexpr int kFFItems = 2;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
+				// 2: 3.59 / 1.27 / 3.61, 4: 3.61 / 1.32 / 3.69, 8: 3.92 / 1.47 / 4.07)
 
-template <bool PHASED>
 __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastState F) {
 	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
@@ -466,118 +465,60 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 	// phase 2: every lane walks rays from the queue; a lane whose ray is decided fetches the next one
 	// at the following leaf step, so lanes stay busy although rays visit different numbers of leaves.
 	const DevTree &T = S.tree;
-	if (PHASED) {
-		// One leaf step per iteration in phases that end with a warp-wide reconvergence (lanes that leave a leaf
-		// list early wait for the scans of the others instead of running NextPoint on their own: ncu showed it
-		// at 11 of 32 lanes), and leaf_visit() runs leaves with and without the shooter's original through the
-		// same bounded any-hit scan (the separate exact scan cost 9.6 % of the instructions at 5.9 lanes).
-		int i = -1, u = 0, ban = 0, prev = -1;
-		unsigned sg = 0;	// leaf lookups so far | "precision exceeded" retries << 11
-		float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, t = 0, ffq = 0;
-		bool done = false;
-		for (;;) {
-			if (i < 0 && !done) {
-				i = atomicAdd(&s_next, 1);
-				if (i >= total) {
-					i = -1, done = true;
-				} else {
-					u = q_u[i], ffq = q_ff[i];
-					const float4 v = __ldg(&S.uv[u]);
-					px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
-					vx = smp.cx - px, vy = smp.cy - py, vz = smp.cz - pz;
-					prev = -1, sg = 0, t = 0.f;
-				}
-			}
-			if (!__any_sync(0xffffffffu, i >= 0)) break;
-			int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
-			int cur = -1;
-			bool visit = false;
-			if (i >= 0) {	// phase A: leaf lookup
-				if ((sg & 0x7ffu) == 0) cur = __ldg(&S.uv_leaf[u]);	// the first probe point is the vertex itself: its leaf is static
-				else cur = leaf_of<false>(T, px + t * vx, py + t * vy, pz + t * vz, nullptr);
-				sg++;
-				if (cur < 0 || (sg & 0x7ffu) > (unsigned)kMaxWalkSteps) {
-					verdict = 0;
-				} else if (prev == cur) {		// raycast.cpp:344-351
-					t = (float)((double)t + 1.0);
-					sg += 1u << 11;
-					if ((sg >> 11) > 100000u) verdict = 0;
-				} else {
-					visit = true;
-				}
-			}
-			__syncwarp();
-			if (visit)	// phase B: the leaf's list
-				verdict = leaf_visit(T, cur, (s_mask[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
-			__syncwarp();
-			if (visit && verdict < 0) {	// phase C: NextPoint (raycast.cpp:235-251)
-				const float4 lo = __ldg(&T.leaf_lo[cur]);
-				const float4 hi = __ldg(&T.leaf_hi[cur]);
-				prev = cur;
-				float tn = 1000000.0f, s;
-				if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
-				if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
-				if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
-				t = (float)((double)tn + 0.1);
-			}
-			if (verdict >= 0) {	// phase D
-				const float ff = verdict ? ffq : 0.0f;
-				if (half) out[u].y = ff; else out[u].x = ff;
-				i = -1;
-			}
-		}
-		return;
-	}
-	int i = -1, u = 0, ban = 0, prev = -1, guard = 0, steps = 0;
-	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, qx = 0, qy = 0, qz = 0, t = 0, ffq = 0;
+	// One leaf step per iteration in phases that end with a warp-wide reconvergence (lanes that leave a leaf
+	// list early wait for the scans of the others instead of running NextPoint on their own: ncu showed it
+	// at 11 of 32 lanes), and leaf_visit() runs leaves with and without the shooter's original through the
+	// same bounded any-hit scan (the separate exact scan cost 9.6 % of the instructions at 5.9 lanes).
+	int i = -1, u = 0, ban = 0, prev = -1;
+	unsigned sg = 0;	// leaf lookups so far | "precision exceeded" retries << 11
+	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, t = 0, ffq = 0;
+	bool done = false;
 	for (;;) {
-		if (i < 0) {
+		if (i < 0 && !done) {
 			i = atomicAdd(&s_next, 1);
-			if (i >= total) break;
-			u = q_u[i], ffq = q_ff[i];
-			const float4 v = __ldg(&S.uv[u]);
-			px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
-			vx = smp.cx - px, vy = smp.cy - py, vz = smp.cz - pz;
-			qx = px, qy = py, qz = pz, prev = -1, guard = 0, steps = 0, t = 0.f;
+			if (i >= total) {
+				i = -1, done = true;
+			} else {
+				u = q_u[i], ffq = q_ff[i];
+				const float4 v = __ldg(&S.uv[u]);
+				px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
+				vx = smp.cx - px, vy = smp.cy - py, vz = smp.cz - pz;
+				prev = -1, sg = 0, t = 0.f;
+			}
 		}
+		if (!__any_sync(0xffffffffu, i >= 0)) break;
 		int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
-		int cur;
-		if (steps == 0) cur = __ldg(&S.uv_leaf[u]);	// the first probe point is the vertex itself: its leaf is static
-		else cur = leaf_of<false>(T, qx, qy, qz, nullptr);
-		if (cur < 0 || ++steps > kMaxWalkSteps) {
-			verdict = 0;
-		} else if (prev == cur) {		// raycast.cpp:344-351
-			t = (float)((double)t + 1.0);
-			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
-			if (++guard > 100000) verdict = 0;
-		} else {
+		int cur = -1;
+		bool visit = false;
+		if (i >= 0) {	// phase A: leaf lookup
+			if ((sg & 0x7ffu) == 0) cur = __ldg(&S.uv_leaf[u]);	// the first probe point is the vertex itself: its leaf is static
+			else cur = leaf_of<false>(T, px + t * vx, py + t * vy, pz + t * vz, nullptr);
+			sg++;
+			if (cur < 0 || (sg & 0x7ffu) > (unsigned)kMaxWalkSteps) {
+				verdict = 0;
+			} else if (prev == cur) {		// raycast.cpp:344-351
+				t = (float)((double)t + 1.0);
+				sg += 1u << 11;
+				if ((sg >> 11) > 100000u) verdict = 0;
+			} else {
+				visit = true;
+			}
+		}
+		__syncwarp();
+		if (visit)	// phase B: the leaf's list
+			verdict = leaf_visit(T, cur, (s_mask[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
+		__syncwarp();
+		if (visit && verdict < 0) {	// phase C: NextPoint (raycast.cpp:235-251)
 			const float4 lo = __ldg(&T.leaf_lo[cur]);
 			const float4 hi = __ldg(&T.leaf_hi[cur]);
-			if ((s_mask[cur >> 5] >> (cur & 31)) & 1u) {
-				int hit = -1;
-				float t_min = 1000000.0f;
-				const int *lp = T.list + __float_as_int(lo.w);
-				int idx;
-				while ((idx = __ldg(lp++)) >= 0) {
-					if (idx == ban) continue;
-					if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
-				}
-				if (hit >= 0) verdict = (hit == logsrc);
-			} else {
-				if (leaf_any_hit(T, __ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban)) verdict = 0;
-			}
-			if (verdict < 0) {	// NextPoint (raycast.cpp:235-251)
-				prev = cur;
-				float tn = 1000000.0f, s;
-				if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
-				if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
-				if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
-				tn = (float)((double)tn + 0.1);
-				qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
-				t = tn;
-			}
+			prev = cur;
+			float tn = 1000000.0f, s;
+			if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
+			if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
+			if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
+			t = (float)((double)tn + 0.1);
 		}
-		if (verdict >= 0) {
+		if (verdict >= 0) {	// phase D
 			const float ff = verdict ? ffq : 0.0f;
 			if (half) out[u].y = ff; else out[u].x = ff;
 			i = -1;

@@ -213,47 +213,6 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 constexpr int kPlaneFlag = 1 << 30;
 constexpr int kIdMask = kPlaneFlag - 1;
 
-// Any-hit scan of one leaf list (int4 chunks of indices, zero-side-plane occluders first): true iff
-// TriListHitted (raycast.cpp:316-333) would return some triangle.  Entries are tested one after the
-// other and the scan stops at the first acceptance (against t_min = 1e6, which is what the reference's
-// first acceptance sees); indices come four per load.
-RADK_HD bool any_hit_one(const DevTree &T, int entry, float px, float py, float pz, float vx, float vy, float vz, int ban) {
-	const int idx = entry & kIdMask;
-	if (idx == ban) return false;
-	const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
-	const float4 q0 = ldg(o), q1 = ldg(o + 1);
-	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
-	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
-	if ((a1 > 0.0f && a2 <= 0.0f) || (a1 < 0.0f && a2 >= 0.0f)) return false;	// t <= 0: certain rejection
-	const float t = a2 / a1;
-	if (t <= 0.0001f) return false;
-	if (t >= 1000000.0f) return false;
-	if (entry & kPlaneFlag) return true;		// all side planes zero: the inside test cannot fail
-	const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
-	const float4 q2 = ldg(o + 2);
-	if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) return false;
-	const float4 q3 = ldg(o + 3);
-	if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) return false;
-	const float4 q4 = ldg(o + 4);
-	if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) return false;
-	return true;
-}
-
-RADK_HD bool leaf_any_hit(const DevTree &T, int list4_off, float px, float py, float pz, float vx, float vy, float vz, int ban) {
-	const int4 *l4 = T.list4 + list4_off;
-	for (;;) {
-		const int4 id = ldg(l4++);
-		if (id.x < 0) return false;
-		if (any_hit_one(T, id.x, px, py, pz, vx, vy, vz, ban)) return true;
-		if (id.y < 0) return false;
-		if (any_hit_one(T, id.y, px, py, pz, vx, vy, vz, ban)) return true;
-		if (id.z < 0) return false;
-		if (any_hit_one(T, id.z, px, py, pz, vx, vy, vz, ban)) return true;
-		if (id.w < 0) return false;
-		if (any_hit_one(T, id.w, px, py, pz, vx, vy, vz, ban)) return true;
-	}
-}
-
 // ---- bounded any-hit: one code path for leaves with and without the shooter's original ----------------
 // TriListHitted (raycast.cpp:316-333) returns the accepted entry with the smallest t, the earliest list
 // position (= smallest index, the lists are ascending) winning ties, because a later entry with
@@ -346,9 +305,9 @@ RADK_HD int leaf_visit(const DevTree &T, int cur, bool lists_src, float px, floa
 	return src_hit ? 1 : -1;
 }
 
-// ray_sees with leaf_visit (the walk of ff_stream_kernel)
+// Is the shooter visible?  Same answer as (ray_walk(...) == logsrc); the walk of ff_batch_kernel.
 template <typename MaskPtr>
-RADK_HD bool ray_sees_bounded(const DevTree &T, MaskPtr has_src, float px, float py, float pz, float vx, float vy, float vz,
+RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, float pz, float vx, float vy, float vz,
 			      int ban, int logsrc) {
 	float t = 0.f;
 	int prev = -1, cur;
@@ -366,50 +325,6 @@ RADK_HD bool ray_sees_bounded(const DevTree &T, MaskPtr has_src, float px, float
 		if (v >= 0) return v == 1;
 		const float4 lo = ldg(&T.leaf_lo[cur]);
 		const float4 hi = ldg(&T.leaf_hi[cur]);
-		prev = cur;
-		float tn = 1000000.0f, s;
-		if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
-		if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
-		if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
-		tn = (float)((double)tn + 0.1);
-		qx = px + tn * vx, qy = py + tn * vy, qz = pz + tn * vz;
-		t = tn;
-	}
-	return false;
-}
-
-template <typename MaskPtr>
-RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, float pz, float vx, float vy, float vz,
-		      int ban, int logsrc) {
-	float t = 0.f;
-	int prev = -1, cur;
-	float qx = px, qy = py, qz = pz;
-	int guard = 0, steps = 0;
-	while ((cur = leaf_of<false>(T, qx, qy, qz, nullptr)) >= 0) {
-		if (++steps > kMaxWalkSteps) return false;
-		if (prev == cur) {		// raycast.cpp:344-351
-			t = (float)((double)t + 1.0);
-			qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
-			if (++guard > 100000) return false;
-			continue;
-		}
-		const float4 lo = ldg(&T.leaf_lo[cur]);
-		const float4 hi = ldg(&T.leaf_hi[cur]);
-		if ((has_src[cur >> 5] >> (cur & 31)) & 1u) {
-			// exact nearest-hit scan (TriListHitted, raycast.cpp:316-333)
-			int hit = -1;
-			float t_min = 1000000.0f;
-			const int *lp = T.list + float_as_int_hd(lo.w);
-			int idx;
-			while ((idx = ldg(lp++)) >= 0) {
-				if (idx == ban) continue;
-				if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
-			}
-			if (hit >= 0) return hit == logsrc;
-		} else {
-			// some other triangle is hit in this leaf: the walk ends, shooter not returned
-			if (leaf_any_hit(T, ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban)) return false;
-		}
 		prev = cur;
 		float tn = 1000000.0f, s;
 		if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }

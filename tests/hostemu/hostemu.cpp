@@ -37,8 +37,7 @@ int emu_rays(const radk_scene *s, const float *p, const float *v, const int *fro
 // Runs `shots` single-source shots the way the kernels do (unique-vertex form factors, then the
 // per-receiver update with the fused argmax) and writes accB[trinum][3][3], deltaB[trinum][3] and
 // the shooter slot of every shot.  counters[0..2] = reference-equivalent rays, visible, shaded receivers.
-static int g_mode = 0;	// 0: cal_ff / ray_walk (per-shot kernels); 1: ff_geom + ray_sees (ff_batch_kernel);
-			// 2: ff_geom + ray_sees_bounded (leaf_visit, the walk of ff_stream_kernel)
+static int g_mode = 0;	// 0: cal_ff / ray_walk (per-shot kernels); 1: ff_geom + ray_sees (leaf_visit, the walk of ff_batch_kernel)
 void emu_set_mode(int mode) { g_mode = mode; }
 
 int emu_run(const radk_scene *s, float converge, int rank, int world, int shots, float *accB, float *deltaB,
@@ -72,7 +71,7 @@ int emu_run(const radk_scene *s, float converge, int rank, int world, int shots,
 	select(&sh);
 	std::vector<unsigned> mask((T.nnodes + 31) / 32);
 	while (done < shots && sh.valid) {
-		if (g_mode >= 1) {	// ff_batch_kernel / ff_stream_kernel: per-row leaf mask, culls first, then the any-hit walk
+		if (g_mode == 1) {	// ff_batch_kernel: per-row leaf mask, culls first, then the any-hit walk
 			std::fill(mask.begin(), mask.end(), 0u);
 			for (int k = T.tri_leaf_begin[sh.logsrc]; k < T.tri_leaf_begin[sh.logsrc + 1]; k++)
 				mask[T.tri_leaves[k] >> 5] |= 1u << (T.tri_leaves[k] & 31);
@@ -90,16 +89,13 @@ int emu_run(const radk_scene *s, float converge, int rank, int world, int shots,
 					const float ff = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, cast);
 					if (!cast) continue;
 					nr++;
-					const bool see = g_mode == 2 ? ray_sees_bounded(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc)
-								     : ray_sees(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc);
-					if (see) out[h] = ff, nv++;
+					if (ray_sees(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc)) out[h] = ff, nv++;
 				}
 				if (sh.splittable) {	// the discarded centre sample, for reference-equivalent counts only
 					float dx, dy, dz;
 					bool cast;
 					ff_geom(sh.centre, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, cast);
-					if (cast) nr++, nv += g_mode == 2 ? ray_sees_bounded(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc)
-								  : ray_sees(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc);
+					if (cast) nr++, nv += ray_sees(T, mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc);
 				}
 				ff0[u] = out[0], ff1[u] = out[1];
 				vstat[u] = nr | (nv << 8);
@@ -237,7 +233,7 @@ extern "C" int emu_start_block_stats(const radk_scene *s, int shooter_slot, long
 				if (sees) return 2;	// the criterion must never kill a visible ray
 			}
 			if (leaf >= 0 && !((mask[leaf >> 5] >> (leaf & 31)) & 1u) && !sees) {
-				if (leaf_any_hit(T, F.leaf_list4[leaf], v.x, v.y, v.z, dx, dy, dz, par)) first_leaf_blocked++;
+				if (leaf_any_hit_bounded(T, F.leaf_list4[leaf], v.x, v.y, v.z, dx, dy, dz, par, 1000000.0f, -1)) first_leaf_blocked++;
 			}
 		}
 	}

@@ -39,11 +39,10 @@ def run_emu(emu, m, shots, rank=0, world=1, converge=1200.0):
     return accB, dB, list(sh[: ns.value]), list(cnt)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name,shots", [("box", 6), ("church", 6), ("blocks", 8), ("sbox", 40), ("model3s", 40)])
 def test_device_core_matches_oracle(hr, po, emu, models_dir, name, shots, mode):
-    """mode 0: cal_ff/ray_walk (per-shot kernels); mode 1: ff_geom + ray_sees (any-hit walk of ff_batch_kernel);
-    mode 2: ff_geom + ray_sees_bounded (bounded any-hit leaf visit of ff_stream_kernel)."""
+    """mode 0: cal_ff/ray_walk (per-shot kernels); mode 1: ff_geom + ray_sees (bounded any-hit leaf visit of ff_batch_kernel)."""
     emu.emu_set_mode(mode)
     m = hr.Model(str(models_dir / f"{name}.tri"))
     sc = oracle_scene(po, m)

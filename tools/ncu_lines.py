@@ -24,21 +24,3 @@ ts = sum(v[0] for v in lines.values()); ti = sum(v[1] for v in lines.values()); 
 print(f"samples {ts}  warp inst {ti}  avg threads {tt/max(ti,1):.2f}")
 for (f, ln), (s, i, t, src) in sorted(lines.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{f:22s}:{ln:4d} inst {100*i/ti:5.1f}%  samples {100*s/ts:5.1f}%  thr {t/max(i,1):5.1f}  {src.strip()[:100]}")
-
-# optional grouping: python tools/ncu_lines.py file.csv N groups  -> share per named line range
-if len(sys.argv) > 3:
-    groups = {}
-    for (f, ln), (s, i, t, src) in lines.items():
-        if f.startswith("ff_stream"):
-            g = ("setup" if ln < 100 else "refill+phase1" if ln < 139 else "fetch" if ln < 156 else "phaseA lookup" if ln < 178 else
-                 "phaseB glue" if ln < 184 else "phaseC nextpoint" if ln < 193 else "phaseD")
-        elif f.startswith("rt_core"):
-            g = ("dot3/ldg helpers" if ln < 90 else "cell lookup" if ln < 127 else "tri_hit (src pretest/exact)" if ln < 150 else
-                 "bounded any-hit" if 260 <= ln < 312 else "leaf_visit glue" if 312 <= ln < 345 else "ff_geom" if ln >= 430 else "other rt_core")
-        else:
-            g = f
-        a = groups.setdefault(g, [0, 0, 0])
-        a[0] += s; a[1] += i; a[2] += t
-    print()
-    for g, (s, i, t) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
-        print(f"{g:30s} inst {100*i/ti:5.1f}%  samples {100*s/ts:5.1f}%  thr {t/max(i,1):5.1f}")
