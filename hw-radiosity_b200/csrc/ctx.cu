@@ -658,6 +658,12 @@ int radk_ctx_reset(radk_ctx *c, const radk_scene *s) {
 		if (e == b) continue;
 		host_parallel_for(e - b, [=](size_t r0, size_t r1) {
 			for (size_t r = b + r0; r < b + r1; r++) {
+				// the records are 236 bytes apart in slot order, the receivers are in Morton order: prefetch ahead
+				if (r + 12 < b + r1) {
+					const radk_triangle &n = s->tri[c->recv_slot[r + 12]];
+					__builtin_prefetch(&n.accB[0][0]);
+					__builtin_prefetch(&n.deltaB[2]);
+				}
 				const radk_triangle &t = s->tri[c->recv_slot[r]];
 				for (int v = 0; v < 3; v++) c->h_stage[v * R + r] = make_float4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
 			}
@@ -917,6 +923,12 @@ int radk_ctx_download(radk_ctx *c, float *accB, float *deltaB, int *parent, int 
 		if (e == b) continue;
 		host_parallel_for(e - b, [=](size_t r0, size_t r1) {
 			for (size_t r = b + r0; r < b + r1; r++) {
+				if (r + 12 < b + r1) {	// scattered stores: fetch the target lines for writing ahead of time
+					const size_t ns = (size_t)c->recv_slot[r + 12];
+					if (accB) { __builtin_prefetch(accB + ns * 9, 1); __builtin_prefetch(accB + ns * 9 + 8, 1); }
+					if (deltaB) __builtin_prefetch(deltaB + ns * 3, 1);
+					if (parent) __builtin_prefetch(parent + ns, 1);
+				}
 				const size_t slot = (size_t)c->recv_slot[r];
 				const float4 a0 = c->h_stage[r], a1 = c->h_stage[R + r], a2 = c->h_stage[2 * R + r];
 				if (accB) {
