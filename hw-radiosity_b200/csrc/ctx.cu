@@ -78,7 +78,7 @@ struct radk_ctx {
 	DevBuf<int> cell_leaf, list, slot_to_recv, shot_log, slot, leaf_list4, tri_leaf_begin, tri_leaves, uv_leaf;
 	DevBuf<int4> list4;
 	DevBuf<unsigned> row_mask;
-	DevBuf<float4> leaf_lo, leaf_hi, occ, geo[3], st[3], st0[3], uv, par_n, par_fk;
+	DevBuf<float4> leaf_box, occ, geo[3], st[3], st0[3], uv, par_n, par_fk;
 	DevBuf<int4> vid;
 	DevBuf<float2> ffh;
 	DevBuf<unsigned> vstat, partial_cnt, ticket;
@@ -248,8 +248,7 @@ int upload_split_scene(radk_ctx *c, const radk_scene *s) {
 	const int frc = flatten_scene(&empty, 0, 1, F);
 	if (frc != RADK_OK) { set_error(F.error); return frc; }
 	CUDA_TRY(c->cell_leaf.upload(F.cell_leaf, st));
-	CUDA_TRY(c->leaf_lo.upload(F.leaf_lo, st));
-	CUDA_TRY(c->leaf_hi.upload(F.leaf_hi, st));
+	CUDA_TRY(c->leaf_box.upload(F.leaf_box, st));
 	CUDA_TRY(c->list.upload(F.list, st));
 	CUDA_TRY(c->list4.upload(F.list4, st));
 	CUDA_TRY(c->leaf_list4.upload(F.leaf_list4, st));
@@ -306,9 +305,9 @@ int upload_split_scene(radk_ctx *c, const radk_scene *s) {
 	CUDA_TRY(cudaMemsetAsync(c->stats.p, 0, sizeof(DevStats), st));
 	CUDA_TRY(cudaMemsetAsync(c->rec.p, 0, (2 + kMaxSources) * sizeof(ShooterRec), st));
 	SplitScene &S = c->SP;
-	S.tree.cell_leaf = c->cell_leaf.p, S.tree.leaf_lo = c->leaf_lo.p, S.tree.leaf_hi = c->leaf_hi.p;
+	S.tree.cell_leaf = c->cell_leaf.p, S.tree.leaf_box = c->leaf_box.p;
 	S.tree.list = c->list.p, S.tree.list4 = c->list4.p, S.tree.leaf_list4 = c->leaf_list4.p;
-	S.tree.tri_leaf_begin = c->tri_leaf_begin.p, S.tree.tri_leaves = c->tri_leaves.p, S.tree.occ = c->occ.p;
+	S.tree.tri_leaf_begin = c->tri_leaf_begin.p, S.tree.tri_leaves = c->tri_leaves.p, S.tree.occ = c->occ.p, S.tree.nocc = s->n0;
 	S.tree.nnodes = s->nnodes;
 	for (int k = 0; k < 3; k++) S.tree.G0[k] = s->G0[k], S.tree.G1[k] = s->G1[k];
 	S.tree.min_grid_len = s->min_grid_len, S.tree.grid_num = s->grid_num, S.tree.inv_min_grid_len = 1.0 / (double)s->min_grid_len;
@@ -394,8 +393,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	c->recv_parent = F.recv_parent;
 	c->h_slot_to_recv = F.slot_to_recv;
 	CUDA_TRY(c->cell_leaf.upload(F.cell_leaf, st));
-	CUDA_TRY(c->leaf_lo.upload(F.leaf_lo, st));
-	CUDA_TRY(c->leaf_hi.upload(F.leaf_hi, st));
+	CUDA_TRY(c->leaf_box.upload(F.leaf_box, st));
 	CUDA_TRY(c->list.upload(F.list, st));
 	CUDA_TRY(c->list4.upload(F.list4, st));
 	CUDA_TRY(c->leaf_list4.upload(F.leaf_list4, st));
@@ -501,13 +499,12 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 
 	DevScene &S = c->S;
 	S.tree.cell_leaf = c->cell_leaf.p;
-	S.tree.leaf_lo = c->leaf_lo.p;
-	S.tree.leaf_hi = c->leaf_hi.p;
+	S.tree.leaf_box = c->leaf_box.p;
 	S.tree.list = c->list.p;
 	S.tree.list4 = c->list4.p, S.tree.leaf_list4 = c->leaf_list4.p;
 	S.tree.tri_leaf_begin = c->tri_leaf_begin.p, S.tree.tri_leaves = c->tri_leaves.p;
 	S.tree.nnodes = s->nnodes;
-	S.tree.occ = c->occ.p;
+	S.tree.occ = c->occ.p, S.tree.nocc = s->n0;
 	for (int k = 0; k < 3; k++) S.tree.G0[k] = s->G0[k], S.tree.G1[k] = s->G1[k];
 	S.tree.min_grid_len = s->min_grid_len;
 	S.tree.grid_num = s->grid_num;
@@ -702,7 +699,7 @@ int radk_ctx_sizes(const radk_ctx *c, int *receivers, int *unique_vertices, int 
 	if (receivers) *receivers = c->R;
 	if (unique_vertices) *unique_vertices = c->U;
 	if (occluders) *occluders = c->n0;
-	if (nodes) *nodes = (int)c->leaf_lo.n;
+	if (nodes) *nodes = (int)(c->leaf_box.n / 2);
 	return RADK_OK;
 }
 

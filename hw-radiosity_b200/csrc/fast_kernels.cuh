@@ -509,8 +509,8 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 			verdict = leaf_visit(T, cur, (s_mask[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
 		__syncwarp();
 		if (visit && verdict < 0) {	// phase C: NextPoint (raycast.cpp:235-251)
-			const float4 lo = __ldg(&T.leaf_lo[cur]);
-			const float4 hi = __ldg(&T.leaf_hi[cur]);
+			const float4 lo = leaf_lo(T, cur);
+			const float4 hi = leaf_hi(T, cur);
 			prev = cur;
 			float tn = 1000000.0f, s;
 			if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }

@@ -29,15 +29,17 @@ namespace radk {
 // reference descent for every cell, so the leaf found is the same by construction.
 struct DevTree {
 	const int *cell_leaf;		// [(grid_num+1)^3], x fastest
-	const float4 *leaf_lo;		// per node: g0.xyz | list offset (int bits)
-	const float4 *leaf_hi;		// per node: g1.xyz | depth (int bits, statistics only)
+	const float4 *leaf_box;		// 2 per node, one 32-byte sector: g0.xyz | list offset (int bits), g1.xyz | depth (int
+					// bits, statistics only) - see leaf_lo() / leaf_hi()
 	const int *list;		// leaf lists, -1 terminated, ascending triangle index
 	const int4 *list4;		// the same lists, each padded with -1 to a multiple of 4 entries (16 B aligned)
 	const int *leaf_list4;		// per node: offset (in int4 units) of its padded list, -1 for inner nodes
 	const int *tri_leaf_begin;	// [n0+1] inverted index: leaves whose list contains triangle i ...
 	const int *tri_leaves;		// ... are tri_leaves[tri_leaf_begin[i] .. tri_leaf_begin[i+1])
 	int nnodes;
-	const float4 *occ;		// 5 float4 per occluder, see OCC_* below
+	const float4 *occ;		// plane parts of all occluders (2 float4 each), then their side-plane parts (3 float4
+					// each): see occ_plane() / occ_side()
+	int nocc;			// number of occluders (= n0)
 	float G0[3], G1[3];
 	float min_grid_len;
 	int grid_num;
@@ -46,9 +48,11 @@ struct DevTree {
 	float cell_eps;			// estimate of a cell coordinate is not trusted (>= 0.25: never trusted)
 };
 // occluder record (the {n, c, se} of TriStore[idx] at shot time, raycast.cpp:288-309):
-//   q0 = n.x n.y n.z c.x | q1 = c.y c.z se00 se01 | q2 = se02 se03 se10 se11
-//   q3 = se12 se13 se20 se21 | q4 = se22 se23 - -
-constexpr int OCC_STRIDE = 5;
+//   plane part  q0 = n.x n.y n.z c.x | q1 = c.y c.z se00 se01
+//   side part   q2 = se02 se03 se10 se11 | q3 = se12 se13 se20 se21 | q4 = se22 se23 - -
+// Most tests end in the plane part (sign of t, t range), so the plane parts are stored densely (four per
+// 128-byte line instead of 1.6 when the 80-byte records were contiguous): more of them stay in L1.
+constexpr int OCC_PLANE = 2, OCC_SIDE = 3;
 // A walk visits at most ~3 * grid_num leaves.  When GridNum is not a power of two (float rounding of
 // (G1-G0)/MinGridLen, e.g. 63) the reference's cell -> leaf descent disagrees with the leaf boxes and its
 // RayHitted can bounce between two leaves forever; the walk is cut after this many leaf lookups and the
@@ -80,6 +84,11 @@ template <typename T> RADK_HD T ldg(const T *p) {
 	return *p;
 #endif
 }
+
+RADK_HD const float4 *occ_plane(const DevTree &T, int idx) { return T.occ + (size_t)idx * OCC_PLANE; }
+RADK_HD const float4 *occ_side(const DevTree &T, int idx) { return T.occ + (size_t)T.nocc * OCC_PLANE + (size_t)idx * OCC_SIDE; }
+RADK_HD float4 leaf_lo(const DevTree &T, int node) { return ldg(&T.leaf_box[2 * (size_t)node]); }
+RADK_HD float4 leaf_hi(const DevTree &T, int node) { return ldg(&T.leaf_box[2 * (size_t)node + 1]); }
 
 // vector.h:36 InnerProd
 RADK_HD float dot3(float ax, float ay, float az, float bx, float by, float bz) {
@@ -120,12 +129,12 @@ RADK_HD int leaf_of(const DevTree &T, float qx, float qy, float qz, WalkCounters
 	gy = gy < 0 ? 0 : (gy > g ? g : gy);
 	gz = gz < 0 ? 0 : (gz > g ? g : gz);
 	const int leaf = ldg(&T.cell_leaf[(gz * dim + gy) * dim + gx]);
-	if (STATS) wc->descent_steps += (unsigned)float_as_int_hd(ldg(&T.leaf_hi[leaf]).w);
+	if (STATS) wc->descent_steps += (unsigned)float_as_int_hd(leaf_hi(T, leaf).w);
 	return leaf;
 }
 
 // TriHitted (raycast.cpp:283-313)
-RADK_HD bool tri_hit(const float4 *o, float px, float py, float pz, float vx, float vy, float vz, float &t_min) {
+RADK_HD bool tri_hit(const float4 *o, const float4 *side, float px, float py, float pz, float vx, float vy, float vz, float &t_min) {
 	const float4 q0 = ldg(o), q1 = ldg(o + 1);
 	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
 	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
@@ -135,11 +144,11 @@ RADK_HD bool tri_hit(const float4 *o, float px, float py, float pz, float vx, fl
 	if (t <= 0.0001f) return false;	// == ((double)t < 0.0001): 0.0001f is the largest float below the double 0.0001
 	if (t >= t_min) return false;
 	const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
-	const float4 q2 = ldg(o + 2);
+	const float4 q2 = ldg(side);
 	if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) return false;
-	const float4 q3 = ldg(o + 3);
+	const float4 q3 = ldg(side + 1);
 	if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) return false;
-	const float4 q4 = ldg(o + 4);
+	const float4 q4 = ldg(side + 2);
 	if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) return false;
 	t_min = t;
 	return true;
@@ -170,8 +179,8 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 			}
 			continue;
 		}
-		const float4 lo = ldg(&T.leaf_lo[cur]);
-		const float4 hi = ldg(&T.leaf_hi[cur]);
+		const float4 lo = leaf_lo(T, cur);
+		const float4 hi = leaf_hi(T, cur);
 		if (STATS) wc->leaf_visits++;
 		// TriListHitted
 		int hit = -1;
@@ -181,7 +190,7 @@ RADK_HD int ray_walk(const DevTree &T, float px, float py, float pz, float vx, f
 		while ((idx = ldg(lp++)) >= 0) {
 			if (idx == ban) continue;
 			if (STATS) wc->tri_tests++;
-			if (tri_hit(T.occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) {
+			if (tri_hit(occ_plane(T, idx), occ_side(T, idx), px, py, pz, vx, vy, vz, t_min)) {
 				if (STATS) wc->tri_accepts++;
 				hit = idx;
 			}
@@ -229,7 +238,7 @@ RADK_HD int any_hit_bounded_one(const DevTree &T, int entry, float px, float py,
 				int ban, float t_max, int tie) {
 	const int idx = entry & kIdMask;
 	if (idx == ban) return 0;
-	const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
+	const float4 *o = occ_plane(T, idx);
 	const float4 q0 = ldg(o), q1 = ldg(o + 1);
 	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
 	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
@@ -239,11 +248,12 @@ RADK_HD int any_hit_bounded_one(const DevTree &T, int entry, float px, float py,
 	if (t > t_max || (t == t_max && idx >= tie)) return 0;
 	if (!(entry & kPlaneFlag)) {	// zero side planes: the inside test cannot fail
 		const float hx = px + t * vx, hy = py + t * vy, hz = pz + t * vz;
-		const float4 q2 = ldg(o + 2);
+		const float4 *sd = occ_side(T, idx);
+		const float4 q2 = ldg(sd);
 		if ((hx * q1.z + hy * q1.w + hz * q2.x + q2.y) < 0.0f) return 0;
-		const float4 q3 = ldg(o + 3);
+		const float4 q3 = ldg(sd + 1);
 		if ((hx * q2.z + hy * q2.w + hz * q3.x + q3.y) < 0.0f) return 0;
-		const float4 q4 = ldg(o + 4);
+		const float4 q4 = ldg(sd + 2);
 		if ((hx * q3.z + hy * q3.w + hz * q4.x + q4.y) < 0.0f) return 0;
 	}
 	return t != t ? 2 : 1;
@@ -274,13 +284,13 @@ __host__ __device__ __noinline__
 #else
 inline
 #endif
-int leaf_visit_exact(const int *lp, const float4 *occ, float px, float py, float pz, float vx, float vy, float vz, int ban, int logsrc) {
+int leaf_visit_exact(const int *lp, const float4 *occ, int nocc, float px, float py, float pz, float vx, float vy, float vz, int ban, int logsrc) {
 	int hit = -1;
 	float t_min = 1000000.0f;
 	int idx;
 	while ((idx = ldg(lp++)) >= 0) {
 		if (idx == ban) continue;
-		if (tri_hit(occ + (size_t)idx * OCC_STRIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
+		if (tri_hit(occ + (size_t)idx * OCC_PLANE, occ + (size_t)nocc * OCC_PLANE + (size_t)idx * OCC_SIDE, px, py, pz, vx, vy, vz, t_min)) hit = idx;
 	}
 	return hit < 0 ? -1 : (hit == logsrc);
 }
@@ -293,13 +303,13 @@ RADK_HD int leaf_visit(const DevTree &T, int cur, bool lists_src, float px, floa
 	int tie = -1;
 	bool src_hit = false;
 	if (lists_src && logsrc != ban) {
-		src_hit = tri_hit(T.occ + (size_t)logsrc * OCC_STRIDE, px, py, pz, vx, vy, vz, t_max);
+		src_hit = tri_hit(occ_plane(T, logsrc), occ_side(T, logsrc), px, py, pz, vx, vy, vz, t_max);
 		if (src_hit) tie = logsrc;
 	}
 	int r = (t_max != t_max) ? 2 : leaf_any_hit_bounded(T, ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban, t_max, tie);
 	if (r == 2) {
 		if (!lists_src) return 0;	// without logsrc in the list any acceptance ends the walk elsewhere
-		return leaf_visit_exact(T.list + float_as_int_hd(ldg(&T.leaf_lo[cur]).w), T.occ, px, py, pz, vx, vy, vz, ban, logsrc);
+		return leaf_visit_exact(T.list + float_as_int_hd(leaf_lo(T, cur).w), T.occ, T.nocc, px, py, pz, vx, vy, vz, ban, logsrc);
 	}
 	if (r == 1) return 0;
 	return src_hit ? 1 : -1;
@@ -323,8 +333,8 @@ RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, flo
 		}
 		const int v = leaf_visit(T, cur, (has_src[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
 		if (v >= 0) return v == 1;
-		const float4 lo = ldg(&T.leaf_lo[cur]);
-		const float4 hi = ldg(&T.leaf_hi[cur]);
+		const float4 lo = leaf_lo(T, cur);
+		const float4 hi = leaf_hi(T, cur);
 		prev = cur;
 		float tn = 1000000.0f, s;
 		if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }

@@ -19,7 +19,8 @@ namespace radk {
 struct FlatScene {
 	// octree
 	std::vector<int> cell_leaf;
-	std::vector<float4> leaf_lo, leaf_hi;
+	std::vector<float4> leaf_lo, leaf_hi;	// host-side views; the device gets them interleaved as leaf_box
+	std::vector<float4> leaf_box;
 	std::vector<int> list;
 	std::vector<int4> list4;
 	std::vector<int> leaf_list4, tri_leaf_begin, tri_leaves;
@@ -37,8 +38,8 @@ struct FlatScene {
 
 	DevTree host_tree(const radk_scene *s) const {	// the same view the kernels get, over host memory
 		DevTree T;
-		T.cell_leaf = cell_leaf.data(), T.leaf_lo = leaf_lo.data(), T.leaf_hi = leaf_hi.data();
-		T.list = list.data(), T.occ = occ.data();
+		T.cell_leaf = cell_leaf.data(), T.leaf_box = leaf_box.data();
+		T.list = list.data(), T.occ = occ.data(), T.nocc = s->n0;
 		T.list4 = list4.data(), T.leaf_list4 = leaf_list4.data();
 		T.tri_leaf_begin = tri_leaf_begin.data(), T.tri_leaves = tri_leaves.data();
 		T.nnodes = (int)leaf_lo.size();
@@ -111,6 +112,8 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 		F.leaf_lo[i] = f4(nd.g0[0], nd.g0[1], nd.g0[2], ibits(nd.list));
 		F.leaf_hi[i] = f4(nd.g1[0], nd.g1[1], nd.g1[2], ibits(depth[i]));
 	}
+	F.leaf_box.resize(2 * (size_t)s->nnodes);
+	for (int i = 0; i < s->nnodes; i++) F.leaf_box[2 * (size_t)i] = F.leaf_lo[i], F.leaf_box[2 * (size_t)i + 1] = F.leaf_hi[i];
 	F.list.assign(s->list, s->list + s->nlist);
 	// padded copies of the leaf lists + inverted index triangle -> leaves
 	F.leaf_list4.assign(s->nnodes, -1);
@@ -146,15 +149,15 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 		F.tri_leaves.insert(F.tri_leaves.end(), leaves_of[i].begin(), leaves_of[i].end());
 	}
 	F.tri_leaf_begin[s->n0] = (int)F.tri_leaves.size();
-	F.occ.resize((size_t)s->n0 * OCC_STRIDE);
+	F.occ.resize((size_t)s->n0 * (OCC_PLANE + OCC_SIDE));
 	for (int i = 0; i < s->n0; i++) {
 		const radk_triangle &t = s->tri[i];
-		float4 *q = &F.occ[(size_t)i * OCC_STRIDE];
+		float4 *q = &F.occ[(size_t)i * OCC_PLANE], *sd = &F.occ[(size_t)s->n0 * OCC_PLANE + (size_t)i * OCC_SIDE];
 		q[0] = f4(t.n[0], t.n[1], t.n[2], t.c[0]);
 		q[1] = f4(t.c[1], t.c[2], t.se[0][0], t.se[0][1]);
-		q[2] = f4(t.se[0][2], t.se[0][3], t.se[1][0], t.se[1][1]);
-		q[3] = f4(t.se[1][2], t.se[1][3], t.se[2][0], t.se[2][1]);
-		q[4] = f4(t.se[2][2], t.se[2][3], 0.f, 0.f);
+		sd[0] = f4(t.se[0][2], t.se[0][3], t.se[1][0], t.se[1][1]);
+		sd[1] = f4(t.se[1][2], t.se[1][3], t.se[2][0], t.se[2][1]);
+		sd[2] = f4(t.se[2][2], t.se[2][3], 0.f, 0.f);
 	}
 
 	// ---- receivers: leaves sorted by (parent, Morton code of the centroid), then sharded

@@ -193,7 +193,7 @@ extern "C" int emu_start_block_stats(const radk_scene *s, int shooter_slot, long
 				for (int e = 0; e < 4 && !end; e++) {
 					if (ids[e] < 0) { end = true; break; }
 					if (!(ids[e] & kPlaneFlag)) continue;
-					const float4 *o = &F.occ[(size_t)(ids[e] & kIdMask) * OCC_STRIDE];
+					const float4 *o = &F.occ[(size_t)(ids[e] & kIdMask) * OCC_PLANE];
 					const double n[3] = {o[0].x, o[0].y, o[0].z}, c[3] = {o[0].w, o[1].x, o[1].y};
 					const double blo[3] = {lo.x, lo.y, lo.z}, bhi[3] = {hi.x, hi.y, hi.z};
 					double pmin = 0, pmax = 0;	// range of p.n over the cell box

@@ -116,14 +116,14 @@ int main(int argc, char **argv) {
 								if (anyhit && !vv.nearest) continue;	// sequential scan would have stopped
 								vv.tests++;
 								// plane part outcome
-								const float4 *o = T.occ + (size_t)idx * OCC_STRIDE;
+								const float4 *o = occ_plane(T, idx);
 								const float a1 = dot3(vx, vy, vz, o[0].x, o[0].y, o[0].z);
 								const float a2 = dot3(o[0].w - px, o[1].x - py, o[1].y - pz, o[0].x, o[0].y, o[0].z);
 								bool plane_ok = !((a1 > 0.0f && a2 <= 0.0f) || (a1 < 0.0f && a2 >= 0.0f));
 								if (plane_ok) { const float tt = a2 / a1; plane_ok = !(tt <= 0.0001f) && !(tt >= 1000000.0f); }
 								if (plane_ok && !(ids[e] & kPlaneFlag)) vv.full++;
 								float tm = vv.nearest ? t_min : 1000000.0f;
-								if (tri_hit(o, px, py, pz, vx, vy, vz, tm)) { anyhit = true; if (vv.nearest) t_min = tm; }
+								if (tri_hit(o, occ_side(T, idx), px, py, pz, vx, vy, vz, tm)) { anyhit = true; if (vv.nearest) t_min = tm; }
 							}
 						}
 						vv.hit = anyhit;
