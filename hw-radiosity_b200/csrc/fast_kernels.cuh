@@ -401,14 +401,14 @@ constexpr int kFFBlock = 256;
 constexpr int kFFItems = 2;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
 				// 2: 3.59 / 1.27 / 3.61, 4: 3.61 / 1.32 / 3.69, 8: 3.92 / 1.47 / 4.07)
 
-__global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastState F) {
+// 6 CTAs per SM (40 registers): measured 4 / 5 / 6 / 8 CTAs per SM on church 4.06 / 3.46 / 3.20 / 3.35 ms (8 = 32 registers, spills)
+__global__ void __launch_bounds__(kFFBlock, 6) ff_batch_kernel(DevScene S, FastState F) {
 	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;
 	const int row = F.todo[j], half = blockIdx.y;
 	__shared__ ShooterRec sh;
 	__shared__ int q_u[kFFBlock * kFFItems];
-	__shared__ float q_ff[kFFBlock * kFFItems];
 	__shared__ int wcount[kFFItems * (kFFBlock / 32)];
 	__shared__ int s_next;
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)(F.rec + row))[threadIdx.x];
@@ -425,22 +425,22 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 		}
 		return;
 	}
-	const FFSample smp = sh.splittable ? sh.half[half] : sh.centre;
-	const int logsrc = sh.logsrc;
-	// phase 1: culls + analytic form factor; survivors are queued in vertex order
-	float ffv[kFFItems];
+	const FFSample *smp = sh.splittable ? &sh.half[half] : &sh.centre;	// stays in shared memory (registers)
+	float *outh = (float *)out + half;	// outh[2 * u] = form factor of vertex u toward this half
+	// phase 1: culls + analytic form factor; survivors are queued in vertex order.  The form factor itself is
+	// stored right away - it is the value if the ray reaches the shooter; a blocked ray zeroes it in phase 2.
 	bool live[kFFItems];
 	unsigned ball[kFFItems];
 #pragma unroll
 	for (int it = 0; it < kFFItems; it++) {
 		const int u = base + it * kFFBlock + threadIdx.x;
-		live[it] = false, ffv[it] = 0.0f;
+		live[it] = false;
 		if (u < S.U) {
 			const float4 v = __ldg(&S.uv[u]);
 			const float4 pn = __ldg(&S.par_n[__float_as_int(v.w)]);
 			float dx, dy, dz;
-			ffv[it] = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live[it]);
-			if (!live[it]) { if (half) out[u].y = 0.0f; else out[u].x = 0.0f; }
+			const float ff = ff_geom(*smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live[it]);
+			outh[2 * (size_t)u] = live[it] ? ff : 0.0f;
 		}
 		ball[it] = __ballot_sync(0xffffffffu, live[it]);
 		if (lane == 0) wcount[it * (kFFBlock / 32) + warp] = __popc(ball[it]);
@@ -455,42 +455,40 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 			if (w < it * (kFFBlock / 32) + warp) off += c;
 			if (it == 0) total += c;
 		}
-		if (live[it]) {
-			const int pos = off + __popc(ball[it] & ((1u << lane) - 1u));
-			q_u[pos] = base + it * kFFBlock + threadIdx.x;
-			q_ff[pos] = ffv[it];
-		}
+		if (live[it]) q_u[off + __popc(ball[it] & ((1u << lane) - 1u))] = base + it * kFFBlock + threadIdx.x;
 	}
 	__syncthreads();
-	// phase 2: every lane walks rays from the queue; a lane whose ray is decided fetches the next one
-	// at the following leaf step, so lanes stay busy although rays visit different numbers of leaves.
+	// phase 2: every lane walks rays from the queue; a lane whose ray is decided fetches the next one at the
+	// following leaf step.  One leaf step per iteration, in sub-phases that each end with a warp-wide reconvergence
+	// (lanes that leave a leaf list early wait for the scans of the others instead of running NextPoint on their
+	// own: ncu showed it at 11 of 32 lanes); leaf_visit() runs leaves with and without the shooter's original
+	// through the same bounded any-hit scan (the separate exact scan cost 9.6 % of the instructions at 5.9 lanes).
+	// The per-lane state is kept small (the probe point is recomputed from t, counters are packed, the sample
+	// point and the result live in shared / global memory): registers decide how many CTAs an SM holds, and
+	// this latency-bound walk gains from every extra warp.
 	const DevTree &T = S.tree;
-	// One leaf step per iteration in phases that end with a warp-wide reconvergence (lanes that leave a leaf
-	// list early wait for the scans of the others instead of running NextPoint on their own: ncu showed it
-	// at 11 of 32 lanes), and leaf_visit() runs leaves with and without the shooter's original through the
-	// same bounded any-hit scan (the separate exact scan cost 9.6 % of the instructions at 5.9 lanes).
-	int i = -1, u = 0, ban = 0, prev = -1;
+	int u = -1, ban = 0, prev = -1;	// u < 0: no ray
 	unsigned sg = 0;	// leaf lookups so far | "precision exceeded" retries << 11
-	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, t = 0, ffq = 0;
-	bool done = false;
+	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, t = 0;
+	bool more = true;
 	for (;;) {
-		if (i < 0 && !done) {
-			i = atomicAdd(&s_next, 1);
+		if (u < 0 && more) {
+			const int i = atomicAdd(&s_next, 1);
 			if (i >= total) {
-				i = -1, done = true;
+				more = false;
 			} else {
-				u = q_u[i], ffq = q_ff[i];
+				u = q_u[i];
 				const float4 v = __ldg(&S.uv[u]);
 				px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
-				vx = smp.cx - px, vy = smp.cy - py, vz = smp.cz - pz;
+				vx = smp->cx - px, vy = smp->cy - py, vz = smp->cz - pz;
 				prev = -1, sg = 0, t = 0.f;
 			}
 		}
-		if (!__any_sync(0xffffffffu, i >= 0)) break;
+		if (!__any_sync(0xffffffffu, u >= 0)) break;
 		int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
 		int cur = -1;
 		bool visit = false;
-		if (i >= 0) {	// phase A: leaf lookup
+		if (u >= 0) {	// phase A: leaf lookup
 			if ((sg & 0x7ffu) == 0) cur = __ldg(&S.uv_leaf[u]);	// the first probe point is the vertex itself: its leaf is static
 			else cur = leaf_of<false>(T, px + t * vx, py + t * vy, pz + t * vz, nullptr);
 			sg++;
@@ -506,7 +504,7 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 		}
 		__syncwarp();
 		if (visit)	// phase B: the leaf's list
-			verdict = leaf_visit(T, cur, (s_mask[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
+			verdict = leaf_visit(T, cur, (s_mask[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, sh.logsrc);
 		__syncwarp();
 		if (visit && verdict < 0) {	// phase C: NextPoint (raycast.cpp:235-251)
 			const float4 lo = leaf_lo(T, cur);
@@ -518,10 +516,9 @@ __global__ void __launch_bounds__(kFFBlock, 5) ff_batch_kernel(DevScene S, FastS
 			if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
 			t = (float)((double)tn + 0.1);
 		}
-		if (verdict >= 0) {	// phase D
-			const float ff = verdict ? ffq : 0.0f;
-			if (half) out[u].y = ff; else out[u].x = ff;
-			i = -1;
+		if (verdict >= 0) {	// phase D: a visible ray keeps the form factor phase 1 stored
+			if (verdict == 0) outh[2 * (size_t)u] = 0.0f;
+			u = -1;
 		}
 	}
 }
