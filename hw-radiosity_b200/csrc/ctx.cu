@@ -443,8 +443,12 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		struct { int rpt; const void *fn; } variants[] = {{1, (const void *)shots_kernel<1>}, {2, (const void *)shots_kernel<2>},
 								 {4, (const void *)shots_kernel<4>}, {0, (const void *)shots_kernel<0>}};
 		c->shots_rpt = -1;
+		// RADK_SHOTS_RPT=0|1|2|4 forces a variant (tests: the streamed variant is otherwise only taken by shards of
+		// more than ~600 k receivers); a forced variant that does not fit falls through to the streamed one
+		const int want_rpt = getenv("RADK_SHOTS_RPT") ? atoi(getenv("RADK_SHOTS_RPT")) : -1;
 		for (auto &v : variants) {
 			int per_sm = 0;
+			if (want_rpt >= 0 && v.rpt != want_rpt && v.rpt != 0) continue;
 			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, kShotsBlock, 0));
 			if (per_sm < 1) continue;
 			per_sm = std::min(per_sm, 2);

@@ -629,20 +629,42 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 				if (kk > key) key = kk, kd0 = ra0[k].w, kd1 = ra1[k].w, kd2 = ra2[k].w;
 			}
 		} else {
-			for (int r = r_begin + threadIdx.x; r < r_end; r += kShotsBlock) {
-				float4 a0 = S.st[0][r], a1 = S.st[1][r], a2 = S.st[2][r];
-				const int slot = __ldg(&S.slot[r]);
-				if (slot == shooter_slot) {
-					a0.w = a1.w = a2.w = 0.0f;
-					S.st[0][r].w = 0.0f, S.st[1][r].w = 0.0f, S.st[2][r].w = 0.0f;
-				} else if (unsaturated(a0, a1, a2)) {
-					const int4 id = __ldg(&S.vid[r]);
-					apply_shot(a0, a1, a2, id, __ldg(&S.par_fk[id.w]), ffrow, sdB0, sdB1, sdB2);
-					S.st[0][r] = a0, S.st[1][r] = a1, S.st[2][r] = a2;
+			// streamed receivers (HBM bound: 96 B of state + 20 B of ids per receiver and shot): kStreamUnroll receivers
+			// per thread are in flight together - all their loads are issued before the first update, the vertex
+			// ids and form-factor gathers of one overlap the state loads of the others
+			constexpr int kStreamUnroll = 4;
+			for (int r0 = r_begin + threadIdx.x; r0 < r_end; r0 += kShotsBlock * kStreamUnroll) {
+				float4 a0[kStreamUnroll], a1[kStreamUnroll], a2[kStreamUnroll], fk[kStreamUnroll];
+				int4 id[kStreamUnroll];
+				int slot[kStreamUnroll];
+#pragma unroll
+				for (int k = 0; k < kStreamUnroll; k++) {
+					const int r = r0 + k * kShotsBlock;
+					slot[k] = -1;
+					if (r < r_end) {
+						a0[k] = S.st[0][r], a1[k] = S.st[1][r], a2[k] = S.st[2][r];
+						slot[k] = __ldg(&S.slot[r]);
+						id[k] = __ldg(&S.vid[r]);
+					}
 				}
-				unsigned c;
-				const unsigned long long kk = candidate_key(S, a0.w, a1.w, a2.w, slot, ~0ull, &c);
-				if (kk > key) key = kk, kd0 = a0.w, kd1 = a1.w, kd2 = a2.w;
+#pragma unroll
+				for (int k = 0; k < kStreamUnroll; k++)
+					if (slot[k] >= 0) fk[k] = __ldg(&S.par_fk[id[k].w]);
+#pragma unroll
+				for (int k = 0; k < kStreamUnroll; k++) {
+					const int r = r0 + k * kShotsBlock;
+					if (slot[k] < 0) continue;
+					if (slot[k] == shooter_slot) {
+						a0[k].w = a1[k].w = a2[k].w = 0.0f;
+						S.st[0][r].w = 0.0f, S.st[1][r].w = 0.0f, S.st[2][r].w = 0.0f;
+					} else if (unsaturated(a0[k], a1[k], a2[k])) {
+						apply_shot(a0[k], a1[k], a2[k], id[k], fk[k], ffrow, sdB0, sdB1, sdB2);
+						S.st[0][r] = a0[k], S.st[1][r] = a1[k], S.st[2][r] = a2[k];
+					}
+					unsigned c;
+					const unsigned long long kk = candidate_key(S, a0[k].w, a1[k].w, a2[k].w, slot[k], ~0ull, &c);
+					if (kk > key) key = kk, kd0 = a0[k].w, kd1 = a1[k].w, kd2 = a2[k].w;
+				}
 			}
 		}
 		if (dbg) { const unsigned long long t = now(); tA += t - tmark; tmark = t; }
