@@ -397,12 +397,13 @@ __global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastStat
 }
 
 // ---- batched form factors -----------------------------------------------------------------------
-constexpr int kFFBlock = 256;
+constexpr int kFFBlock = 128;	// small CTAs: 128 x 2 vertices (measured 64 / 128 / 256 / 512 threads: church 3.37 / 3.19 / 3.23 / 3.51 ms)
 constexpr int kFFItems = 2;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
 				// 2: 3.59 / 1.27 / 3.61, 4: 3.61 / 1.32 / 3.69, 8: 3.92 / 1.47 / 4.07)
 
-// 6 CTAs per SM (40 registers): measured 4 / 5 / 6 / 8 CTAs per SM on church 4.06 / 3.46 / 3.20 / 3.35 ms (8 = 32 registers, spills)
-__global__ void __launch_bounds__(kFFBlock, 6) ff_batch_kernel(DevScene S, FastState F) {
+// 48 warps per SM (40 registers): measured 32 / 40 / 48 / 64 warps per SM on church 4.06 / 3.46 / 3.20 / 3.35 ms (64 = 32
+// registers, spills)
+__global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(DevScene S, FastState F) {
 	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;

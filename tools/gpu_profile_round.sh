@@ -1,7 +1,7 @@
 #!/bin/bash
 # Evidence for profiles/: launch list + one ncu --set full capture of the dominant kernel + plain bench lines.
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_church.csv python bench.py --steps 2 --warmup 1 > gpurun_out/launches_run.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 585 -c 200 --csv --log-file gpurun_out/launches_church.csv python bench.py --steps 2 --warmup 1 > gpurun_out/launches_run.log 2>&1
 KREGEX=ff_batch OUT=prof_ff_final bash tools/ncu_ff.sh
 ncu --set full --clock-control none --import-source on -k regex:shots_kernel -s 3 -c 1 -f -o gpurun_out/prof_shots_final python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_shots_run.log 2>&1
 for wl in church box room synth1m; do
@@ -9,10 +9,10 @@ for wl in church box room synth1m; do
   tail -c 300 gpurun_out/bench_${wl}.err
 done
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_church_reference_arm.json 2> gpurun_out/bench_ref.err
-RADK_HOST_THREADS=16 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_church_ht16.json 2>/dev/null
+
 python - <<'PY'
 import json
-for n in ("church", "box", "room", "synth1m", "church_ht16"):
+for n in ("church", "box", "room", "synth1m"):
     try:
         d = json.load(open(f"gpurun_out/bench_{n}.json"))
         print(n, round(d["ms_per_step"], 3), d["roofline"]["kernel_ms_per_step"], "frac", round(d["roofline"]["frac"], 3), "e2e", d["e2e"])
