@@ -308,9 +308,9 @@ def run_ours(args):
 
     hbm_gbs, peak_src, sm_max = measured_peaks()
     hbm_gbs *= world               # aggregate peaks of the N GPUs the job runs on
-    traffic = None                 # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+    traffic_rec = {}               # DRAM bytes per launch of the dominant kernel, from the committed ncu capture (1 GPU)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+        traffic_rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
     except (OSError, ValueError):
         pass
     # dominant kernel: the visibility / form-factor kernel (K3a: ff_batch_kernel).  Algorithmic bytes per launch =
@@ -321,6 +321,7 @@ def run_ours(args):
     algo_bytes_per_step = ALGO_BYTES_PER_RECEIVER * recv_shaded
     dom = "ff_batch_kernel (K3a: culls + form factor + octree walk)" if ff_ms >= upd_ms else "shots_kernel (K3b+K1)"
     dom_ms = max(ff_ms, upd_ms)
+    traffic = traffic_rec.get("dram_bytes_per_launch") if world == 1 and dom.startswith(traffic_rec.get("kernel", "?")) else None
     achieved = algo_bytes_per_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # FP32 side of the SURVEY section 8(d) roofline, counted per traced ray by the device itself
     flops = (35 * walk["calff"] + 12 * walk["leaf_visits"] + 6 * walk["descent_steps"] + 22 * (walk["leaf_visits"] - walk["tri_accepts"] * 0)
