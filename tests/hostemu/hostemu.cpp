@@ -34,6 +34,23 @@ int emu_rays(const radk_scene *s, const float *p, const float *v, const int *fro
 	return 0;
 }
 
+// ray_sees (bounded any-hit leaf visits, the walk of ff_batch_kernel) for n rays, each toward its own shooter
+// original logsrc[i]: out[i] = 1 iff the walk ends on logsrc[i].  nan_visits counts rays whose walk accepted a NaN t
+// (the order-dependent case that falls back to the sequential scan).
+int emu_sees(const radk_scene *s, const float *p, const float *v, const int *from, const int *logsrc, int n, int *out) {
+	FlatScene F;
+	if (flatten_scene(s, 0, 1, F)) { fprintf(stderr, "emu: %s\n", F.error.c_str()); return 1; }
+	const DevTree T = F.host_tree(s);
+	std::vector<unsigned> mask((T.nnodes + 31) / 32);
+	for (int i = 0; i < n; i++) {
+		std::fill(mask.begin(), mask.end(), 0u);
+		for (int k = T.tri_leaf_begin[logsrc[i]]; k < T.tri_leaf_begin[logsrc[i] + 1]; k++)
+			mask[T.tri_leaves[k] >> 5] |= 1u << (T.tri_leaves[k] & 31);
+		out[i] = ray_sees(T, mask.data(), p[3 * i], p[3 * i + 1], p[3 * i + 2], v[3 * i], v[3 * i + 1], v[3 * i + 2], from[i], logsrc[i]);
+	}
+	return 0;
+}
+
 // Runs `shots` single-source shots the way the kernels do (unique-vertex form factors, then the
 // per-receiver update with the fused argmax) and writes accB[trinum][3][3], deltaB[trinum][3] and
 // the shooter slot of every shot.  counters[0..2] = reference-equivalent rays, visible, shaded receivers.
