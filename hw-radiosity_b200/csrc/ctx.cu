@@ -342,7 +342,7 @@ int split_one_shot(radk_ctx *c, bool *converged) {
 	while (n > prev) {
 		const int count = n - prev;
 		const int nb = (count + kScanBlock - 1) / kScanBlock;
-		split_shade_kernel<<<(count + 127) / 128, 128, 0, st>>>(c->SP, sh, prev, n);
+		split_shade_kernel<<<(count + kSplitBlock / kSplitGroup - 1) / (kSplitBlock / kSplitGroup), kSplitBlock, 0, st>>>(c->SP, sh, prev, n);
 		split_scan_sums_kernel<<<nb, kScanBlock, 0, st>>>(c->SP, prev, n);
 		split_scan_offsets_kernel<<<1, kScanBlock, 0, st>>>(c->SP, nb, c->sp_growth.p);
 		split_append_kernel<<<nb, kScanBlock, 0, st>>>(c->SP, sh, prev, n, n);
@@ -365,11 +365,14 @@ int split_one_shot(radk_ctx *c, bool *converged) {
 			}
 			grown = off;
 		}
+		const bool device_advanced = n + growth + 4 < c->SP.limit;	// split_scan_offsets_kernel already moved trinum
 		prev = n;
 		n += grown;
 		c->sp_host_trinum = n;
-		CUDA_TRY(cudaMemcpyAsync(c->sp_trinum.p, &c->sp_host_trinum, sizeof(int), cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaStreamSynchronize(st));
+		if (!device_advanced) {
+			CUDA_TRY(cudaMemcpyAsync(c->sp_trinum.p, &c->sp_host_trinum, sizeof(int), cudaMemcpyHostToDevice, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+		}
 	}
 	split_finish_shot_kernel<<<1, 1, 0, st>>>(c->SP, sh);
 	c->launches++;

@@ -91,16 +91,33 @@ __device__ __forceinline__ void split_cal_radiosity(const ShooterRec &sh, const 
 	a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
 }
 
-// Shade (shade.cpp:435-525) for the slots [lo, hi) of this round.
-__global__ void __launch_bounds__(128) split_shade_kernel(SplitScene S, const ShooterRec *__restrict__ shp, int lo, int hi) {
+// Shade (shade.cpp:435-525) for the slots [lo, hi) of this round.  kSplitGroup lanes work on one slot: lanes 0-2
+// evaluate the three vertex form factors, lane 3 the centre sample, then all lanes take the random interior samples
+// eight at a time.  The serial loop stops at the first sample whose form factor leaves the plane by more than
+// DeltaFFLimit; the group finds that sample with a ballot and only counts the rays the serial loop would have cast,
+// so decisions, radiosity and statistics equal a one-thread-per-slot evaluation (one slot used to take up to
+// (4 + area/SampleArea) x 3 octree walks in sequence: 2.2 ms for the first round of a shot on blocks.tri).
+constexpr int kSplitGroup = 8;
+constexpr int kSplitBlock = 128;
+
+__device__ __forceinline__ void add_counters(FFCounters &fc, WalkCounters &wc, const FFCounters &f, const WalkCounters &w) {
+	fc.calff += f.calff, fc.rays += f.rays, fc.visible += f.visible;
+	wc.traced += w.traced, wc.leaf_visits += w.leaf_visits, wc.descent_steps += w.descent_steps, wc.tri_tests += w.tri_tests;
+	wc.tri_accepts += w.tri_accepts, wc.precision_exceeded += w.precision_exceeded, wc.guard_trips += w.guard_trips;
+}
+
+__global__ void __launch_bounds__(kSplitBlock) split_shade_kernel(SplitScene S, const ShooterRec *__restrict__ shp, int lo, int hi) {
 	__shared__ ShooterRec sh;
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)shp)[threadIdx.x];
 	__syncthreads();
-	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	const int gl = threadIdx.x % kSplitGroup;	// lane within the slot's group
+	const int i = lo + blockIdx.x * (kSplitBlock / kSplitGroup) + threadIdx.x / kSplitGroup;
+	const int gshift = (threadIdx.x & 31) / kSplitGroup * kSplitGroup;
+	const unsigned gmask = ((1u << kSplitGroup) - 1u) << gshift;
 	FFCounters fc = {0, 0, 0};
 	WalkCounters wc = {0, 0, 0, 0, 0, 0, 0};
 	unsigned shaded = 0u;
-	if (i < hi) S.count[i] = 0;
+	if (gl == 0 && i < hi) S.count[i] = 0;
 	if (sh.valid && i < hi) {
 		const float4 g0 = S.p[0][i], g1 = S.p[1][i], g2 = S.p[2][i];
 		const int parent = __float_as_int(g0.w);
@@ -108,38 +125,63 @@ __global__ void __launch_bounds__(128) split_shade_kernel(SplitScene S, const Sh
 		const bool unsat = a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
 				   a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f;
 		if (parent >= 0 && i != sh.slot && unsat) {	// rad.cpp:420-428
-			shaded = 1u;
+			shaded = gl == 0 ? 1u : 0u;
 			const float4 pn = S.n[i];
 			const float area = g1.w;
-			float ff[3];
-			ff[0] = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, g0.x, g0.y, g0.z, &fc, &wc);
-			ff[1] = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, g1.x, g1.y, g1.z, &fc, &wc);
-			ff[2] = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, g2.x, g2.y, g2.z, &fc, &wc);
-			bool split = false;
-			float ffs = 0.0f;
 			// shade.cpp:455-466: too small to split, or no room in the pool (re-checked exactly at append time)
-			if (!(area < S.area_limit) && !((double)area < 1e-8) && !(*S.trinum + 4 >= S.limit)) {
-				float ground = (float)((double)(ff[0] + ff[1] + ff[2]) / 3.0);
-				const float cx = (float)((double)(g0.x + g1.x + g2.x) / 3.0), cy = (float)((double)(g0.y + g1.y + g2.y) / 3.0),
-					    cz = (float)((double)(g0.z + g1.z + g2.z) / 3.0);
-				ffs = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, cx, cy, cz, &fc, &wc);
-				float deltaff = fabsf(ground - ffs);
+			const bool try_split = !(area < S.area_limit) && !((double)area < 1e-8) && !(*S.trinum + 4 >= S.limit);
+			// lanes 0-2: the vertices, lane 3: the centre (only when a split is possible)
+			const float cx = (float)((double)(g0.x + g1.x + g2.x) / 3.0), cy = (float)((double)(g0.y + g1.y + g2.y) / 3.0),
+				    cz = (float)((double)(g0.z + g1.z + g2.z) / 3.0);
+			float fv = 0.0f;
+			if (gl < 3 || (gl == 3 && try_split)) {
+				const float qx = gl == 0 ? g0.x : gl == 1 ? g1.x : gl == 2 ? g2.x : cx;
+				const float qy = gl == 0 ? g0.y : gl == 1 ? g1.y : gl == 2 ? g2.y : cy;
+				const float qz = gl == 0 ? g0.z : gl == 1 ? g1.z : gl == 2 ? g2.z : cz;
+				fv = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, qx, qy, qz, &fc, &wc);
+			}
+			float ff[3];
+			ff[0] = __shfl_sync(gmask, fv, 0, kSplitGroup), ff[1] = __shfl_sync(gmask, fv, 1, kSplitGroup);
+			ff[2] = __shfl_sync(gmask, fv, 2, kSplitGroup);
+			const float ffs = __shfl_sync(gmask, fv, 3, kSplitGroup);
+			bool split = false;
+			if (try_split) {
+				const float ground0 = (float)((double)(ff[0] + ff[1] + ff[2]) / 3.0);
+				float dlast = fabsf(ground0 - ffs);	// deltaff of the serial loop after its last evaluation
 				split = true;
-				if (deltaff < S.delta_ff) {
+				if (dlast < S.delta_ff) {
 					const int samples = (int)(area / S.sample_area);
-					for (int k = 0; k < samples; k++) {	// GetPointInTriangle (shade.cpp:49-68) with hashed weights
-						float r1 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k) >> 1);
-						float r2 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k + 1u) >> 1);
-						float r3 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k + 2u) >> 1);
-						const float tot = r1 + r2 + r3;
-						r1 /= tot, r2 /= tot, r3 /= tot;
-						const float sx = r1 * g0.x + r2 * g1.x + r3 * g2.x, sy = r1 * g0.y + r2 * g1.y + r3 * g2.y,
-							    sz = r1 * g0.z + r2 * g1.z + r3 * g2.z;
-						ground = r1 * ff[0] + r2 * ff[1] + r3 * ff[2];
-						const float f = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, sx, sy, sz, &fc, &wc);
-						if ((deltaff = fabsf(ground - f)) > S.delta_ff) break;
+					bool exceeded = false;
+					for (int kb = 0; kb < samples && !exceeded; kb += kSplitGroup) {
+						const int k = kb + gl;
+						float d = 0.0f;
+						bool ex = false;
+						FFCounters f1 = {0, 0, 0};
+						WalkCounters w1 = {0, 0, 0, 0, 0, 0, 0};
+						if (k < samples) {	// GetPointInTriangle (shade.cpp:49-68) with hashed weights
+							float r1 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k) >> 1);
+							float r2 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k + 1u) >> 1);
+							float r3 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k + 2u) >> 1);
+							const float tot = r1 + r2 + r3;
+							r1 /= tot, r2 /= tot, r3 /= tot;
+							const float sx = r1 * g0.x + r2 * g1.x + r3 * g2.x, sy = r1 * g0.y + r2 * g1.y + r3 * g2.y,
+								    sz = r1 * g0.z + r2 * g1.z + r3 * g2.z;
+							const float ground = r1 * ff[0] + r2 * ff[1] + r3 * ff[2];
+							const float f = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, sx, sy, sz, &f1, &w1);
+							d = fabsf(ground - f);
+							ex = d > S.delta_ff;
+						}
+						const unsigned exm = (__ballot_sync(gmask, ex) >> gshift) & ((1u << kSplitGroup) - 1u);
+						const int first = exm ? __ffs(exm) - 1 : kSplitGroup;	// the serial loop breaks here
+						if (k < samples && gl <= first) add_counters(fc, wc, f1, w1);
+						if (exm) {
+							exceeded = true;
+						} else {
+							const int last = min(kSplitGroup - 1, samples - 1 - kb);
+							dlast = __shfl_sync(gmask, d, last, kSplitGroup);
+						}
 					}
-					if (deltaff < S.delta_ff) split = false;	// smooth enough
+					if (!exceeded && dlast < S.delta_ff) split = false;	// smooth enough
 				}
 				if (split) {	// PartitionTriangleWithCenterAndStore's shape refusals (shade.cpp:265-275)
 					float maxLen = 0.0f, minLen = 1e+30f;
@@ -153,12 +195,14 @@ __global__ void __launch_bounds__(128) split_shade_kernel(SplitScene S, const Sh
 					if ((double)(minLen / maxLen) < 1e-1 || minLen < 1) split = false;
 				}
 			}
-			if (!split) {
-				split_cal_radiosity(sh, S.fk[i], ff, a0, a1, a2);
-				S.st[0][i] = a0, S.st[1][i] = a1, S.st[2][i] = a2;
-			} else {
-				S.count[i] = (parent == i) ? 3 : 2;
-				S.ffs[i] = make_float4(ff[0], ff[1], ff[2], ffs);
+			if (gl == 0) {
+				if (!split) {
+					split_cal_radiosity(sh, S.fk[i], ff, a0, a1, a2);
+					S.st[0][i] = a0, S.st[1][i] = a1, S.st[2][i] = a2;
+				} else {
+					S.count[i] = (parent == i) ? 3 : 2;
+					S.ffs[i] = make_float4(ff[0], ff[1], ff[2], ffs);
+				}
 			}
 		}
 	}
@@ -209,7 +253,13 @@ __global__ void __launch_bounds__(kScanBlock) split_scan_offsets_kernel(SplitSce
 		if (threadIdx.x == 0) carry += total;
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) *growth = carry;
+	if (threadIdx.x == 0) {
+		*growth = carry;
+		// every request of this round is granted when even the last one finds room (isFullPool(4), shade.cpp:262):
+		// the pool size is advanced here; otherwise the host works out the granted prefix and uploads it
+		const int n = *S.trinum;
+		if (n + carry + 4 < S.limit) *S.trinum = n + carry;
+	}
 }
 
 // ---- stream-compacted append (center split, shade.cpp:261-306 + 213-241) ------------------------------
