@@ -525,13 +525,23 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 }
 
 // ---- persistent shot loop -----------------------------------------------------------------------
+// Arrival with release semantics (publishes what the calling thread wrote before, i.e. its CTA's partial record) and
+// waiting with acquire loads: no separate MEMBAR.GPU on either side (church: 4.8 -> 4.5 us per shot).
+__device__ __forceinline__ void barrier_arrive(unsigned *counter) {
+	asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void barrier_wait(const unsigned *counter, unsigned target) {
+	unsigned v;
+	do {
+		asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+	} while (v < target);
+}
+// Called by every thread after a __syncthreads() that ends the CTA's work of the shot; thread 0 has written the
+// CTA's record.
 __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
-	__syncthreads();
 	if (threadIdx.x == 0) {
-		__threadfence();
-		atomicAdd(counter, 1u);
-		while (*((volatile unsigned *)counter) < target) { }
-		__threadfence();
+		barrier_arrive(counter);
+		barrier_wait(counter, target);
 	}
 	__syncthreads();
 }
@@ -723,12 +733,9 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			// rank; every CTA (on every rank) then waits for all ranks' mail in its own box.
 			const unsigned tag = (unsigned)F.epoch * 0x9E3779B1u + (unsigned)(shots_before + done + 1);	// never equals a stale slot's tag
 			__syncthreads();
-			if (threadIdx.x == 0) { __threadfence(); atomicAdd(F.barrier, 1u); }
+			if (threadIdx.x == 0) barrier_arrive(F.barrier);
 			if (blockIdx.x == 0) {
-				if (threadIdx.x == 0) {
-					while (*((volatile unsigned *)F.barrier) < epoch * (unsigned)nctas) { }
-					__threadfence();
-				}
+				if (threadIdx.x == 0) barrier_wait(F.barrier, epoch * (unsigned)nctas);
 				__syncthreads();
 				unsigned long long k = 0ull;
 				int who = -1;
