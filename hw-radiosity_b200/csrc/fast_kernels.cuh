@@ -536,16 +536,6 @@ __device__ __forceinline__ void barrier_wait(const unsigned *counter, unsigned t
 		asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
 	} while (v < target);
 }
-// Called by every thread after a __syncthreads() that ends the CTA's work of the shot; thread 0 has written the
-// CTA's record.
-__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
-	if (threadIdx.x == 0) {
-		barrier_arrive(counter);
-		barrier_wait(counter, target);
-	}
-	__syncthreads();
-}
-
 constexpr int kShotsBlock = 512;
 
 // CalRadiosity (shade.cpp:244-259) of one receiver from cached vertex form factors.
@@ -580,7 +570,6 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 	__shared__ float s_dB[kShotsBlock / 32][3];
 	__shared__ Partial s_best;
 	__shared__ int s_row_slot[kMaxRows];			// cache directory: slot held by each row
-	__shared__ int s_next_row;
 	constexpr int NR = RPT > 0 ? RPT : 1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nctas = gridDim.x;
@@ -590,7 +579,6 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 	if (threadIdx.x == 0) {
 		cur = *F.handoff;
 		if (cur.valid) cur.row = F.slot_row[cur.slot];
-		s_next_row = -1;
 	}
 	if (threadIdx.x < kMaxRows) s_row_slot[threadIdx.x] = threadIdx.x < F.rows ? F.row_slot[threadIdx.x] : -1;
 	// resident receivers
@@ -695,7 +683,9 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 				Partial p;
 				p.key = m, p.dB[0] = s_dB[w][0], p.dB[1] = s_dB[w][1], p.dB[2] = s_dB[w][2], p.pad = 0;
 				s_best = p;
-				if (F.world > 1) F.partial[parity * max_ctas + blockIdx.x] = p;
+				F.partial[parity * max_ctas + blockIdx.x] = p;
+				// single GPU: the CTA's record is final here - arrive at the grid barrier right away
+				if (F.world == 1) barrier_arrive(F.barrier);
 			}
 		}
 		__syncthreads();	// s_key / s_dB are reused below
@@ -705,9 +695,9 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			// (identical `cur` everywhere, no second barrier).  The whole 32-byte record comes with one pair of
 			// 128-bit loads, and the winner's cache row is looked up in the shared-memory directory, so the
 			// barrier is followed by a single L2 round trip.
-			if (threadIdx.x == 0) F.partial[parity * max_ctas + blockIdx.x] = s_best;
 			if (dbg) { const unsigned long long t = now(); tB += t - tmark; tmark = t; }
-			grid_barrier(F.barrier, epoch * (unsigned)nctas);
+			if (threadIdx.x == 0) barrier_wait(F.barrier, epoch * (unsigned)nctas);
+			__syncthreads();
 			if (dbg) { const unsigned long long t = now(); tC += t - tmark; tmark = t; }
 			unsigned long long k = 0ull;
 			float d0 = 0.f, d1 = 0.f, d2 = 0.f;
@@ -721,11 +711,16 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			if (lane == 0) s_key[warp] = m1;
 			__syncthreads();
 			const unsigned long long m = warp_max_u64(lane < kShotsBlock / 32 ? s_key[lane] : 0ull);	// every warp reduces the warp maxima
-			if (m != 0ull && k == m) s_best.key = m, s_best.dB[0] = d0, s_best.dB[1] = d1, s_best.dB[2] = d2;
-			if (threadIdx.x == 0 && m == 0ull) s_best.key = 0ull;
-			if (warp == 0) {	// cache directory lookup from shared memory
+			// the next shooter is written in place: slot and unshot energy by the thread that holds the winning record,
+			// its cache row (shared-memory directory) by warp 0 - one barrier ends the shot
+			if (m != 0ull && k == m) cur.slot = (int)(m & 0xffffffffu), cur.dB[0] = d0, cur.dB[1] = d1, cur.dB[2] = d2, cur.valid = 1;
+			if (warp == 0) {
 				const unsigned hit = __ballot_sync(0xffffffffu, m != 0ull && s_row_slot[lane] == (int)(m & 0xffffffffu));
-				if (lane == 0) s_next_row = hit ? __ffs(hit) - 1 : -1;
+				if (lane == 0) {
+					if (blockIdx.x == 0) S.sel.shot_log[(shots_before + done) % S.sel.shot_log_cap] = shooter_slot;
+					cur.row = hit ? __ffs(hit) - 1 : -1;
+					if (m == 0ull) cur.slot = -1, cur.row = -1, cur.dB[0] = cur.dB[1] = cur.dB[2] = 0.0f, cur.valid = 0;
+				}
 			}
 			__syncthreads();
 		} else {
@@ -782,26 +777,24 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 				s_best = best;
 			}
 			__syncthreads();
-		}
-		if (threadIdx.x == 0) {
-			if (blockIdx.x == 0) S.sel.shot_log[(shots_before + done) % S.sel.shot_log_cap] = shooter_slot;
-			ShotRec n;
-			n.pad[0] = n.pad[1] = 0;
-			if (s_best.key == 0ull) {
-				n.slot = -1, n.row = -1, n.dB[0] = n.dB[1] = n.dB[2] = 0.0f, n.valid = 0;
-			} else {
-				n.slot = (int)(s_best.key & 0xffffffffu);
-				n.row = -1;
-				if (F.world == 1) n.row = s_next_row;
-				else
+			if (threadIdx.x == 0) {
+				if (blockIdx.x == 0) S.sel.shot_log[(shots_before + done) % S.sel.shot_log_cap] = shooter_slot;
+				ShotRec n;
+				n.pad[0] = n.pad[1] = 0;
+				if (s_best.key == 0ull) {
+					n.slot = -1, n.row = -1, n.dB[0] = n.dB[1] = n.dB[2] = 0.0f, n.valid = 0;
+				} else {
+					n.slot = (int)(s_best.key & 0xffffffffu);
+					n.row = -1;
 					for (int j = 0; j < F.rows; j++)
 						if (s_row_slot[j] == n.slot) n.row = j;
-				n.dB[0] = s_best.dB[0], n.dB[1] = s_best.dB[1], n.dB[2] = s_best.dB[2];
-				n.valid = 1;
+					n.dB[0] = s_best.dB[0], n.dB[1] = s_best.dB[1], n.dB[2] = s_best.dB[2];
+					n.valid = 1;
+				}
+				cur = n;
 			}
-			cur = n;
+			__syncthreads();
 		}
-		__syncthreads();
 		if (dbg) { const unsigned long long t = now(); tD += t - tmark; tmark = t; }
 		done++, budget--, parity ^= 1;
 	}
