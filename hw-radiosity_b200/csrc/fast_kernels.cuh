@@ -684,8 +684,8 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 				p.key = m, p.dB[0] = s_dB[w][0], p.dB[1] = s_dB[w][1], p.dB[2] = s_dB[w][2], p.pad = 0;
 				s_best = p;
 				F.partial[parity * max_ctas + blockIdx.x] = p;
-				// single GPU: the CTA's record is final here - arrive at the grid barrier right away
-				if (F.world == 1) barrier_arrive(F.barrier);
+				// the CTA's record is final here - arrive at the (local) grid barrier right away
+				barrier_arrive(F.barrier);
 			}
 		}
 		__syncthreads();	// s_key / s_dB are reused below
@@ -727,8 +727,6 @@ __global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(De
 			// multi-GPU: CTA 0 waits for the local CTAs, reduces their partials and mails the rank's best to every
 			// rank; every CTA (on every rank) then waits for all ranks' mail in its own box.
 			const unsigned tag = (unsigned)F.epoch * 0x9E3779B1u + (unsigned)(shots_before + done + 1);	// never equals a stale slot's tag
-			__syncthreads();
-			if (threadIdx.x == 0) barrier_arrive(F.barrier);
 			if (blockIdx.x == 0) {
 				if (threadIdx.x == 0) barrier_wait(F.barrier, epoch * (unsigned)nctas);
 				__syncthreads();
