@@ -215,7 +215,6 @@ int reset_fast_state(radk_ctx *c) {
 // ev (optional): 4 events recorded around the three kernels, for profiling.
 int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	cudaStream_t st = c->stream;
-	CUDA_TRY(cudaMemsetAsync(c->F.barrier, 0, sizeof(unsigned), st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
 	predict_kernel<<<64, 1024, 0, st>>>(c->S, c->F);
 	if (c->F.world > 1) { predict_merge_kernel<<<1, 256, 0, st>>>(c->S, c->F); c->launches++; }

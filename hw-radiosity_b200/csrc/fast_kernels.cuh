@@ -100,7 +100,7 @@ struct FastState {
 	unsigned *ticket;
 	ShotRec *handoff;		// current shooter between kernels
 	Partial *partial;		// [2][max CTAs], 32-byte records
-	unsigned *barrier;		// grid barrier counter (zeroed before each shots launch)
+	unsigned *barrier;		// grid barrier counter (zeroed by the last CTA of predict_kernel before each shots launch)
 	long long *budget;		// shots the current radk_ctx_step call may still run
 	unsigned *row_mask;		// [rows][mask_words] bit n set <=> leaf n's list contains the row's logsrc
 	int mask_words;
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence();
+	if (threadIdx.x == 0) *F.barrier = 0u;	// the round's shots_kernel counts its grid barriers from zero
 	dbg_stamp(F, 1);
 	// ---- last CTA: the `rows` largest group maxima.  Threads 0..255 own eight keys each; per round a thread
 	// maximum, an 8-warp reduction and one named barrier of 256 threads - the other 24 warps wait below.
