@@ -455,12 +455,16 @@ RADK_HD void make_shooter(const float p[3][3], float nx, float ny, float nz, flo
 
 // AdaptCalFF(CalFF(centre)) as it executes (shade.cpp:141-168, stray ';' at 164): for a splittable
 // shooter the value is CalFF(t1)+CalFF(t2); the centre sample only matters for the statistics.
+// adapt_ff_sub evaluates one of its three independent parts so that cooperating lanes can take one each:
+//   sub 0: the centre sample (the value for an unsplittable shooter; statistics only otherwise),
+//   sub 1 / 2: CalFF toward half t1 / t2 (0 for an unsplittable shooter).
 template <bool STATS>
-RADK_HD float adapt_ff(const DevTree &T, const ShooterRec &sh, float ndx, float ndy, float ndz, float desLen,
-		       int logdest, float px, float py, float pz, FFCounters *fc, WalkCounters *wc) {
+RADK_HD float adapt_ff_sub(const DevTree &T, const ShooterRec &sh, int sub, float ndx, float ndy, float ndz, float desLen,
+			   int logdest, float px, float py, float pz, FFCounters *fc, WalkCounters *wc) {
 	if (!sh.splittable)
-		return cal_ff<STATS>(T, sh.centre, sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
-	if (STATS) {	// reference-equivalent counting of the discarded centre sample (no walk needed)
+		return sub == 0 ? cal_ff<STATS>(T, sh.centre, sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc) : 0.0f;
+	if (sub != 0) return cal_ff<STATS>(T, sh.half[sub - 1], sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
+	if (STATS) {	// reference-equivalent counting of the discarded centre sample (no walk counters)
 		fc->calff++;
 		const float dx = sh.centre.cx - px, dy = sh.centre.cy - py, dz = sh.centre.cz - pz;
 		const float dotSrc = dot3(dx, dy, dz, sh.centre.nx, sh.centre.ny, sh.centre.nz);
@@ -479,8 +483,16 @@ RADK_HD float adapt_ff(const DevTree &T, const ShooterRec &sh, float ndx, float 
 			}
 		}
 	}
-	const float f1 = cal_ff<STATS>(T, sh.half[0], sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
-	const float f2 = cal_ff<STATS>(T, sh.half[1], sh.logsrc, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
+	return 0.0f;
+}
+
+template <bool STATS>
+RADK_HD float adapt_ff(const DevTree &T, const ShooterRec &sh, float ndx, float ndy, float ndz, float desLen,
+		       int logdest, float px, float py, float pz, FFCounters *fc, WalkCounters *wc) {
+	const float f0 = adapt_ff_sub<STATS>(T, sh, 0, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
+	if (!sh.splittable) return f0;
+	const float f1 = adapt_ff_sub<STATS>(T, sh, 1, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
+	const float f2 = adapt_ff_sub<STATS>(T, sh, 2, ndx, ndy, ndz, desLen, logdest, px, py, pz, fc, wc);
 	return f1 + f2;
 }
 

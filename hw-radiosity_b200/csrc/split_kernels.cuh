@@ -91,19 +91,28 @@ __device__ __forceinline__ void split_cal_radiosity(const ShooterRec &sh, const 
 	a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
 }
 
-// Shade (shade.cpp:435-525) for the slots [lo, hi) of this round.  kSplitGroup lanes work on one slot: lanes 0-2
-// evaluate the three vertex form factors, lane 3 the centre sample, then all lanes take the random interior samples
-// eight at a time.  The serial loop stops at the first sample whose form factor leaves the plane by more than
-// DeltaFFLimit; the group finds that sample with a ballot and only counts the rays the serial loop would have cast,
-// so decisions, radiosity and statistics equal a one-thread-per-slot evaluation (one slot used to take up to
-// (4 + area/SampleArea) x 3 octree walks in sequence: 2.2 ms for the first round of a shot on blocks.tri).
-constexpr int kSplitGroup = 8;
+// Shade (shade.cpp:435-525) for the slots [lo, hi) of this round.  kSplitGroup lanes work on one slot and every
+// form factor is evaluated by three of them (adapt_ff_sub: centre sample, half t1, half t2 - three independent octree
+// walks): lanes 0-11 take the three vertices and the centre sample, then the random interior samples go five at a time.
+// The serial loop stops at the first sample whose form factor leaves the plane by more than DeltaFFLimit; the group
+// finds that sample with a ballot and only counts the rays the serial loop would have cast, so decisions, radiosity
+// and statistics equal a one-thread-per-slot evaluation (one slot used to take up to (4 + area/SampleArea) x 3
+// walks in sequence: 2.2 ms for the first round of a shot on blocks.tri).
+constexpr int kSplitGroup = 16;
 constexpr int kSplitBlock = 128;
+constexpr int kSplitBatch = kSplitGroup / 3;	// interior samples per pass
 
 __device__ __forceinline__ void add_counters(FFCounters &fc, WalkCounters &wc, const FFCounters &f, const WalkCounters &w) {
 	fc.calff += f.calff, fc.rays += f.rays, fc.visible += f.visible;
 	wc.traced += w.traced, wc.leaf_visits += w.leaf_visits, wc.descent_steps += w.descent_steps, wc.tri_tests += w.tri_tests;
 	wc.tri_accepts += w.tri_accepts, wc.precision_exceeded += w.precision_exceeded, wc.guard_trips += w.guard_trips;
+}
+
+// value of point q (lanes 3q .. 3q+2 of the group hold its three parts)
+__device__ __forceinline__ float group_ff(unsigned gmask, float part, int q, bool splittable) {
+	const float v0 = __shfl_sync(gmask, part, 3 * q, kSplitGroup), v1 = __shfl_sync(gmask, part, 3 * q + 1, kSplitGroup),
+		    v2 = __shfl_sync(gmask, part, 3 * q + 2, kSplitGroup);
+	return splittable ? v1 + v2 : v0;
 }
 
 __global__ void __launch_bounds__(kSplitBlock) split_shade_kernel(SplitScene S, const ShooterRec *__restrict__ shp, int lo, int hi) {
@@ -114,6 +123,7 @@ __global__ void __launch_bounds__(kSplitBlock) split_shade_kernel(SplitScene S, 
 	const int i = lo + blockIdx.x * (kSplitBlock / kSplitGroup) + threadIdx.x / kSplitGroup;
 	const int gshift = (threadIdx.x & 31) / kSplitGroup * kSplitGroup;
 	const unsigned gmask = ((1u << kSplitGroup) - 1u) << gshift;
+	const int q = gl / 3, sub = gl - 3 * q;		// point and part this lane evaluates (q < 5)
 	FFCounters fc = {0, 0, 0};
 	WalkCounters wc = {0, 0, 0, 0, 0, 0, 0};
 	unsigned shaded = 0u;
@@ -128,22 +138,23 @@ __global__ void __launch_bounds__(kSplitBlock) split_shade_kernel(SplitScene S, 
 			shaded = gl == 0 ? 1u : 0u;
 			const float4 pn = S.n[i];
 			const float area = g1.w;
+			const bool splittable = sh.splittable != 0;
 			// shade.cpp:455-466: too small to split, or no room in the pool (re-checked exactly at append time)
 			const bool try_split = !(area < S.area_limit) && !((double)area < 1e-8) && !(*S.trinum + 4 >= S.limit);
-			// lanes 0-2: the vertices, lane 3: the centre (only when a split is possible)
+			// points 0-2: the vertices, point 3: the centre (only when a split is possible)
 			const float cx = (float)((double)(g0.x + g1.x + g2.x) / 3.0), cy = (float)((double)(g0.y + g1.y + g2.y) / 3.0),
 				    cz = (float)((double)(g0.z + g1.z + g2.z) / 3.0);
-			float fv = 0.0f;
-			if (gl < 3 || (gl == 3 && try_split)) {
-				const float qx = gl == 0 ? g0.x : gl == 1 ? g1.x : gl == 2 ? g2.x : cx;
-				const float qy = gl == 0 ? g0.y : gl == 1 ? g1.y : gl == 2 ? g2.y : cy;
-				const float qz = gl == 0 ? g0.z : gl == 1 ? g1.z : gl == 2 ? g2.z : cz;
-				fv = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, qx, qy, qz, &fc, &wc);
+			float part = 0.0f;
+			if (q < 3 || (q == 3 && try_split)) {
+				const float qx = q == 0 ? g0.x : q == 1 ? g1.x : q == 2 ? g2.x : cx;
+				const float qy = q == 0 ? g0.y : q == 1 ? g1.y : q == 2 ? g2.y : cy;
+				const float qz = q == 0 ? g0.z : q == 1 ? g1.z : q == 2 ? g2.z : cz;
+				part = adapt_ff_sub<true>(S.tree, sh, sub, pn.x, pn.y, pn.z, pn.w, parent, qx, qy, qz, &fc, &wc);
 			}
 			float ff[3];
-			ff[0] = __shfl_sync(gmask, fv, 0, kSplitGroup), ff[1] = __shfl_sync(gmask, fv, 1, kSplitGroup);
-			ff[2] = __shfl_sync(gmask, fv, 2, kSplitGroup);
-			const float ffs = __shfl_sync(gmask, fv, 3, kSplitGroup);
+			ff[0] = group_ff(gmask, part, 0, splittable), ff[1] = group_ff(gmask, part, 1, splittable);
+			ff[2] = group_ff(gmask, part, 2, splittable);
+			const float ffs = group_ff(gmask, part, 3, splittable);
 			bool split = false;
 			if (try_split) {
 				const float ground0 = (float)((double)(ff[0] + ff[1] + ff[2]) / 3.0);
@@ -152,13 +163,13 @@ __global__ void __launch_bounds__(kSplitBlock) split_shade_kernel(SplitScene S, 
 				if (dlast < S.delta_ff) {
 					const int samples = (int)(area / S.sample_area);
 					bool exceeded = false;
-					for (int kb = 0; kb < samples && !exceeded; kb += kSplitGroup) {
-						const int k = kb + gl;
-						float d = 0.0f;
-						bool ex = false;
+					for (int kb = 0; kb < samples && !exceeded; kb += kSplitBatch) {
+						const int k = kb + q;
+						const bool mine = q < kSplitBatch && k < samples;
+						float ground = 0.0f, spart = 0.0f;
 						FFCounters f1 = {0, 0, 0};
 						WalkCounters w1 = {0, 0, 0, 0, 0, 0, 0};
-						if (k < samples) {	// GetPointInTriangle (shade.cpp:49-68) with hashed weights
+						if (mine) {	// GetPointInTriangle (shade.cpp:49-68) with hashed weights
 							float r1 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k) >> 1);
 							float r2 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k + 1u) >> 1);
 							float r3 = (float)(hash3((unsigned)S.shot_no, (unsigned)i, 3u * k + 2u) >> 1);
@@ -166,19 +177,20 @@ __global__ void __launch_bounds__(kSplitBlock) split_shade_kernel(SplitScene S, 
 							r1 /= tot, r2 /= tot, r3 /= tot;
 							const float sx = r1 * g0.x + r2 * g1.x + r3 * g2.x, sy = r1 * g0.y + r2 * g1.y + r3 * g2.y,
 								    sz = r1 * g0.z + r2 * g1.z + r3 * g2.z;
-							const float ground = r1 * ff[0] + r2 * ff[1] + r3 * ff[2];
-							const float f = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, sx, sy, sz, &f1, &w1);
-							d = fabsf(ground - f);
-							ex = d > S.delta_ff;
+							ground = r1 * ff[0] + r2 * ff[1] + r3 * ff[2];
+							spart = adapt_ff_sub<true>(S.tree, sh, sub, pn.x, pn.y, pn.z, pn.w, parent, sx, sy, sz, &f1, &w1);
 						}
+						const float f = group_ff(gmask, spart, q < kSplitBatch ? q : 0, splittable);
+						const float d = mine ? fabsf(ground - f) : 0.0f;
+						const bool ex = mine && d > S.delta_ff;
 						const unsigned exm = (__ballot_sync(gmask, ex) >> gshift) & ((1u << kSplitGroup) - 1u);
-						const int first = exm ? __ffs(exm) - 1 : kSplitGroup;	// the serial loop breaks here
-						if (k < samples && gl <= first) add_counters(fc, wc, f1, w1);
+						const int first = exm ? (__ffs(exm) - 1) / 3 : kSplitBatch;	// sample at which the serial loop breaks
+						if (mine && q <= first) add_counters(fc, wc, f1, w1);
 						if (exm) {
 							exceeded = true;
 						} else {
-							const int last = min(kSplitGroup - 1, samples - 1 - kb);
-							dlast = __shfl_sync(gmask, d, last, kSplitGroup);
+							const int last = min(kSplitBatch - 1, samples - 1 - kb);
+							dlast = __shfl_sync(gmask, d, 3 * last, kSplitGroup);
 						}
 					}
 					if (!exceeded && dlast < S.delta_ff) split = false;	// smooth enough
