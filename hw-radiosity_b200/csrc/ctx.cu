@@ -345,7 +345,8 @@ int split_one_shot(radk_ctx *c, bool *converged) {
 		split_scan_sums_kernel<<<nb, kScanBlock, 0, st>>>(c->SP, prev, n);
 		split_scan_offsets_kernel<<<1, kScanBlock, 0, st>>>(c->SP, nb, c->sp_growth.p);
 		split_append_kernel<<<nb, kScanBlock, 0, st>>>(c->SP, sh, prev, n, n);
-		c->launches += 4;
+		split_reshade_kernel<<<(count * 4 + 127) / 128, 128, 0, st>>>(c->SP, sh, prev, n);
+		c->launches += 5;
 		int growth = 0;
 		CUDA_TRY(cudaMemcpyAsync(&growth, c->sp_growth.p, sizeof(int), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
@@ -358,9 +359,10 @@ int split_one_shot(radk_ctx *c, bool *converged) {
 			CUDA_TRY(cudaMemcpy(cnt.data(), c->sp_count.p + prev, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
 			int off = 0;
 			for (int k = 0; k < count; k++) {
-				if (cnt[k] == 0) continue;
+				const int ck = cnt[k] == kReshade ? 2 : cnt[k];	// granted in-place splits were re-marked by the append kernel
+				if (ck == 0) continue;
 				if (n + off + 4 >= c->SP.limit) break;
-				off += cnt[k];
+				off += ck;
 			}
 			grown = off;
 		}

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kSplitBlock) split_shade_kernel(SplitScene S, 
 
 // ---- exclusive scan of count[lo, hi): per-CTA sums, then one CTA scans the sums ----------------------
 constexpr int kScanBlock = 256;
+constexpr int kReshade = -2;	// count[] mark: child replaced in place, to be re-shaded by split_reshade_kernel
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
 	__shared__ int wsum[kScanBlock / 32];
@@ -343,19 +344,44 @@ __global__ void __launch_bounds__(kScanBlock) split_append_kernel(SplitScene S, 
 				S.p[0][i].w = __int_as_float(-1);
 				S.rec[i].parent = -1;
 			} else {
-				// replaced in place by t3 and shaded at once with ff2 = {ff0, ff1, FF at the new vertex} (shade.cpp:509-520)
+				// replaced in place by t3 and shaded at once with ff2 = {ff0, ff1, FF at the new vertex} (shade.cpp:509-520):
+				// split_reshade_kernel does that with three lanes per slot; the slot is marked for it
 				split_write_child(S, t3, i, q, a0, a1, a2, parent, -1, t1, t2);
-				const float4 pn = S.n[i];
-				float ff2[3] = {f.x, f.y, 0.0f};
-				ff2[2] = adapt_ff<true>(S.tree, sh, pn.x, pn.y, pn.z, pn.w, parent, c[0], c[1], c[2], &fc, &wc);
-				split_cal_radiosity(sh, S.fk[i], ff2, a0, a1, a2);
-				S.st[0][i] = a0, S.st[1][i] = a1, S.st[2][i] = a2;
+				S.count[i] = kReshade;
 			}
 		}
 	}
 	flush_counters(S.stats, fc, wc, 0u);
 	const unsigned s = __reduce_add_sync(0xffffffffu, nsplit);
 	if ((threadIdx.x & 31) == 0 && s) atomicAdd(&S.stats->splits, (unsigned long long)s);
+}
+
+// The in-place children of this round (count == kReshade): form factor at the new vertex (the centroid, vertex 2 of the
+// child), CalRadiosity with {ff0, ff1, that} (shade.cpp:509-520).  Four lanes per slot, three of them walk.
+__global__ void __launch_bounds__(128) split_reshade_kernel(SplitScene S, const ShooterRec *__restrict__ shp, int lo, int hi) {
+	__shared__ ShooterRec sh;
+	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)shp)[threadIdx.x];
+	__syncthreads();
+	const int sub = threadIdx.x & 3;
+	const int i = lo + (blockIdx.x * 128 + threadIdx.x) / 4;
+	const unsigned gmask = 0xfu << ((threadIdx.x & 31) & ~3);
+	FFCounters fc = {0, 0, 0};
+	WalkCounters wc = {0, 0, 0, 0, 0, 0, 0};
+	if (i < hi && S.count[i] == kReshade) {
+		const float4 g0 = S.p[0][i], g2 = S.p[2][i], pn = S.n[i];
+		const int parent = __float_as_int(g0.w);
+		float part = 0.0f;
+		if (sub < 3) part = adapt_ff_sub<true>(S.tree, sh, sub, pn.x, pn.y, pn.z, pn.w, parent, g2.x, g2.y, g2.z, &fc, &wc);
+		const float v0 = __shfl_sync(gmask, part, 0, 4), v1 = __shfl_sync(gmask, part, 1, 4), v2 = __shfl_sync(gmask, part, 2, 4);
+		if (sub == 0) {
+			const float4 f = S.ffs[i];
+			const float ff2[3] = {f.x, f.y, sh.splittable ? v1 + v2 : v0};
+			float4 a0 = S.st[0][i], a1 = S.st[1][i], a2 = S.st[2][i];
+			split_cal_radiosity(sh, S.fk[i], ff2, a0, a1, a2);
+			S.st[0][i] = a0, S.st[1][i] = a1, S.st[2][i] = a2;
+		}
+	}
+	flush_counters(S.stats, fc, wc, 0u);
 }
 
 // end of a shot: the shooter's unshot energy is spent (rad.cpp:446-449), bookkeeping
