@@ -8,8 +8,10 @@
 //  * children inherit n, Frgb, deltaB and interpolated accB; Brgb, se, deltaaccB keep the slot's
 //    previous contents (zero for never-used slots);
 //  * the cross-link test at shade.cpp:416 compares array addresses and is therefore always false.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
-#include <set>
+#include <queue>
 #include <utility>
 #include "model.hpp"
 
@@ -18,7 +20,7 @@ namespace {
 
 struct Splitter {
 	Model &m;
-	radk_triangle *T;	// m.tri.data(); the pool never reallocates during refinement
+	radk_triangle *T;	// the refinement pool (fixed for the whole run)
 
 	bool pool_full(int need) const { return m.trinum + need >= m.pool_limit(); }	// shade.cpp:26-30
 	int alloc() { return m.trinum++; }	// shade.cpp:14-25 (exhaustion is excluded by pool_full(4))
@@ -134,35 +136,39 @@ struct Splitter {
 }  // namespace
 
 void prepartition(Model &m) {
-	// the pool must not move while slots reference each other by index only - but reserve anyway
-	// so that T stays valid: children are written in place.
+	// The refinement runs in a calloc'ed pool of the reference's size: never-used slots are all-zero like the
+	// reference's BSS, but only the pages that get written are ever touched (filling a 236 MB vector took longer
+	// than the refinement itself); the live slots move into m.tri at the end.
 	const int limit = m.pool_limit();
-	if ((int)m.tri.size() < limit) {
-		radk_triangle zero;
-		memset(&zero, 0, sizeof(zero));
-		m.tri.resize((size_t)limit, zero);	// never-used slots are all-zero, like the reference's BSS
-	}
-	Splitter sp{m, m.tri.data()};
-	std::set<std::pair<float, int>> work;
+	const size_t cap = (size_t)std::max(limit, m.trinum);
+	radk_triangle *pool = (radk_triangle *)calloc(cap, sizeof(radk_triangle));
+	if (!pool) return;	// out of memory: the mesh stays unrefined
+	memcpy(pool, m.tri.data(), (size_t)m.trinum * sizeof(radk_triangle));
+	Splitter sp{m, pool};
+	// The reference keeps its work list in a std::set<pair<area, slot>> and takes *rbegin().  A binary heap pops the
+	// same sequence as long as the set never has to merge two equal pairs - and it never does: a slot is only pushed
+	// again when one of its children takes its place, with exactly half the area it had at its previous push, so all
+	// entries of one slot differ in area (fresh slots are pushed once).
+	std::priority_queue<std::pair<float, int>> work;
 	for (int i = 0; i < m.trinum; i++) {
-		const radk_triangle &t = m.tri[i];
+		const radk_triangle &t = pool[i];
 		if (t.area < 1.f || is_light(t)) continue;
-		work.insert(std::make_pair(t.area, i));
+		work.push(std::make_pair(t.area, i));
 	}
 	while (!work.empty()) {		// the reference dereferences rbegin() of an empty set here (UB)
-		std::pair<float, int> top = *work.rbegin();
-		work.erase(top);
+		const std::pair<float, int> top = work.top();
+		work.pop();
 		const int slot = top.second;
 		// opts.prepartition == 2 (synthetic scaling scenes only): keep going where the reference gives up
 		const bool exhaustive = m.opts.prepartition == 2;
-		if (m.tri[slot].area < 1) { if (exhaustive) continue; break; }
+		if (pool[slot].area < 1) { if (exhaustive) continue; break; }
 		int child[4];
 		if (sp.split(slot, child) < 0) { if (exhaustive && !sp.pool_full(4)) continue; break; }
-		if (is_light(m.tri[slot])) {	// shade.cpp:580-590
-			const radk_triangle &t = m.tri[slot];
+		if (is_light(pool[slot])) {	// shade.cpp:580-590
+			const radk_triangle &t = pool[slot];
 			for (int i = 0; i < 4; i++) {
 				if (child[i] < 0) continue;
-				radk_triangle &ch = m.tri[child[i]];
+				radk_triangle &ch = pool[child[i]];
 				for (int k = 0; k < 3; k++) ch.Brgb[k] = t.Brgb[k];
 				for (int v = 0; v < 3; v++) {
 					for (int k = 0; k < 3; k++) ch.accB[v][k] = t.accB[v][k];
@@ -171,8 +177,10 @@ void prepartition(Model &m) {
 			}
 		}
 		for (int i = 0; i < 4; i++)
-			if (child[i] >= 0) work.insert(std::make_pair(m.tri[child[i]].area, child[i]));
+			if (child[i] >= 0) work.push(std::make_pair(pool[child[i]].area, child[i]));
 	}
+	m.tri.assign(pool, pool + m.trinum);
+	free(pool);
 }
 
 }  // namespace radk
