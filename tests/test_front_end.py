@@ -121,3 +121,19 @@ def test_poly_input_equals_sibling_tri(hr, golden, models_dir, name):
 def test_malformed_poly(hr):
     with pytest.raises(hr.RadkError):
         hr.Model(text=b"101 101 101 0 0 0 4\n0 0 0\n1 0 0\n")
+
+
+@pytest.mark.parametrize("mode,trinum,digest", [
+    (1, 49774, "4760a300890462d1d0f928fb56a0d6fe24b59281f2f3ccf6b010897f9f8a2383"),
+    (2, 195201, "294cf25d6526d117f8f60c78d2fe6f7d5c69cc9cb4b5635239c12a9baf2cc375"),
+])
+def test_prepartition_of_synthetic_scene_is_pinned(hr, tmp_path, mode, trinum, digest):
+    """The seeded synthetic room (bench config 5) through PrePartition as the reference runs it (1) and through the
+    exhaustive variant the scaling scenes use (2): pins the work-list order (largest area first, larger slot on ties)
+    - these digests were produced with the reference's std::set work list and must survive any faster structure."""
+    from hw_radiosity_b200 import synth
+    p = tmp_path / "s.tri"
+    p.write_bytes(synth.room_scene(60000, seed=3))
+    m = hr.Model(str(p), prepartition=mode, tri_limit=4000000, max_tri=4000000)
+    assert m.trinum == trinum
+    assert hashlib.sha256(np.ascontiguousarray(m.triangles).tobytes()).hexdigest() == digest
