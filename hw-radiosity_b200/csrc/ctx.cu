@@ -220,7 +220,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	if (c->F.world > 1) { predict_merge_kernel<<<1, 256, 0, st>>>(c->S, c->F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
-	ff_batch_kernel<<<g, kFFBlock, (size_t)c->F.mask_words * sizeof(unsigned), st>>>(c->S, c->F);
+	ff_batch_kernel<<<g, kFFBlock, 0, st>>>(c->S, c->F);
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	int max_ctas = c->shots_ctas;
 	void *args[] = {(void *)&c->S, (void *)&c->F, (void *)&max_ctas};

@@ -405,7 +405,6 @@ constexpr int kFFItems = 2;	// candidate vertices per thread before compaction (
 // 48 warps per SM (40 registers): measured 32 / 40 / 48 / 64 warps per SM on church 4.06 / 3.46 / 3.20 / 3.35 ms (64 = 32
 // registers, spills)
 __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(DevScene S, FastState F) {
-	extern __shared__ unsigned s_mask[];	// [mask_words] leaves that list the shooter's original
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;
 	const int row = F.todo[j], half = blockIdx.y;
@@ -414,7 +413,7 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 	__shared__ int wcount[kFFItems * (kFFBlock / 32)];
 	__shared__ int s_next;
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)(F.rec + row))[threadIdx.x];
-	for (int w = threadIdx.x; w < F.mask_words; w += kFFBlock) s_mask[w] = F.row_mask[(size_t)row * F.mask_words + w];
+	const unsigned *row_mask = F.row_mask + (size_t)row * F.mask_words;	// bit n: leaf n lists the shooter's original (read through L1)
 	if (threadIdx.x == 0) s_next = 0;
 	__syncthreads();
 	float2 *out = F.ff + (size_t)row * S.U;
@@ -506,7 +505,7 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 		}
 		__syncwarp();
 		if (visit)	// phase B: the leaf's list
-			verdict = leaf_visit(T, cur, (s_mask[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, sh.logsrc);
+			verdict = leaf_visit(T, cur, (__ldg(&row_mask[cur >> 5]) >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, sh.logsrc);
 		__syncwarp();
 		if (visit && verdict < 0) {	// phase C: NextPoint (raycast.cpp:235-251)
 			const float4 lo = leaf_lo(T, cur);
