@@ -50,11 +50,12 @@ class ModelOpts(C.Structure):
 
 
 STATS_FIELDS = ["shots", "rays", "visible", "calff", "traced_rays", "leaf_visits", "descent_steps", "tri_tests",
-                "tri_accepts", "precision_exceeded", "receivers", "splits", "kernel_launches", "ray_guard_trips"]
+                "tri_accepts", "precision_exceeded", "receivers", "splits", "kernel_launches", "ray_guard_trips",
+                "ff_rows_filled", "rounds", "shots_scheduled", "rounds_reapplied"]
 
 
 class Stats(C.Structure):
-    _fields_ = [(n, C.c_longlong) for n in STATS_FIELDS] + [("reserved", C.c_longlong * 4)]
+    _fields_ = [(n, C.c_longlong) for n in STATS_FIELDS]
 
 
 # every symbol include/radk.h declares (tests check the library exports all of them)

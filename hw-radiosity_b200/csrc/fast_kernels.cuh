@@ -3,20 +3,24 @@
 // Observation: the form factors of a shot depend only on WHICH patch shoots (pure geometry on a
 // frozen mesh), not on the radiosity state; only the cheap per-receiver update is serial from shot
 // to shot.  And the next shooters are predictable: they are (almost always) the patches with the
-// largest unshot energy now.  So the loop is split into rounds of three kernels:
+// largest unshot energy now.  So the loop runs in rounds of five kernels, no host round trip in between:
 //
 //   predict_kernel   top-K candidates by unshot energy (exact top-1 + per-group maxima), form-factor
 //                    cache rows assigned to the ones not cached yet, their shooter records built (K2).
 //   ff_batch_kernel  K3a for all new rows at once: (row, half, unique vertex) items; facing culls first,
-//                    survivors compacted through shared memory so every lane of a warp walks a ray;
-//                    K x 2U rays per launch fill the 148 SMs and hide the walk's dependent-load latency.
-//   shots_kernel     persistent cooperative kernel, one CTA per SM slot: up to `budget` shots, each =
-//                    K3b update from the cached row + block argmax + ONE grid barrier + every CTA
-//                    reducing the per-CTA partials redundantly (K1).  It returns when the next shooter
-//                    has no cached row (misprediction), on convergence, or when the budget is spent.
+//                    survivors compacted through shared memory so every lane of a warp walks a ray.
+//   chain_kernel     one CTA: collects the candidates' own records (state + the form factors between the
+//                    candidates), replays the shots on those 32 records alone and writes the schedule
+//                    (shot_core.cuh).  Multi-GPU: each candidate's owner publishes its record to every rank.
+//   apply_kernel     K3b for the whole schedule in one pass over the receivers (state read once per round, the
+//                    form-factor gathers of all shots independent of each other), leaves a copy of the old state
+//                    and the index of the first shot after which a non-candidate overtakes (first violation).
+//   commit_kernel    shots up to the first violation are the reference's; if the schedule went further the valid
+//                    prefix is re-applied from the copy.  Bookkeeping (shot log, budget).
 //
 // Results are bit-identical to the per-shot kernels of shoot_kernels.cuh: same arithmetic, same
-// selection rule; prediction only decides which form factors are ready, never which patch shoots.
+// selection rule; prediction only decides which form factors are ready and which shots can be batched,
+// never which patch shoots.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -25,9 +29,8 @@
 namespace radk {
 
 constexpr int kPredictGroups = 2048;	// groups for the approximate top-K (= 2 keys per thread of the last CTA)
-constexpr int kMaxRows = 32;		// upper bound of form-factor cache rows (one ballot word)
 
-struct ShotRec {		// the shooter of the next shot, handed from shot to shot / kernel to kernel
+struct ShotRec {		// the shooter of the next shot as the prediction sees it (diagnostics)
 	int slot;		// TriStore slot, -1 none
 	int row;		// cache row holding its form factors, -1 = not cached
 	float dB[3];		// its unshot energy at selection time (what CalRadiosity multiplies by)
@@ -35,58 +38,35 @@ struct ShotRec {		// the shooter of the next shot, handed from shot to shot / ke
 	int pad[2];
 };
 
-struct alignas(32) Partial {	// one CTA's best candidate of a shot
-	unsigned long long key;
-	float dB[3];
-	int pad;
-};
-
 // ---- multi-GPU mailboxes (one PeerBox per rank, in that rank's HBM, mapped into every peer) ---------
-// Ranks exchange (a) per round: their local top candidates with full shooter records, (b) per shot:
-// their local best (key, deltaB).  Writers store the payload, __threadfence_system(), then a sequence
-// number (run epoch << 40 | round or shot number); readers spin on the sequence number in their OWN
-// box (local memory), so a wait costs one NVLink store latency.  Payload slots are double-buffered by
-// parity: a writer can be at most one round / one shot ahead of the slowest reader.
+// Three exchanges per round, none per shot: (a) the ranks' local top candidates with full shooter records,
+// (b) each candidate's record (state + form factors between the candidates) from the rank that owns it,
+// (c) each rank's first violation of the round's schedule.  (a) and (b): the writer stores the payload,
+// fence.sc.sys (__threadfence_system), then a sequence number (run epoch << 40 | round); readers spin on the
+// sequence number in their OWN box (local memory) and fence before reading the payload - the release / acquire
+// pattern of the PTX memory model.  (c) is a single 64-bit word (tag | value), one store.  Slots are
+// double-buffered by round parity: a writer can be at most one round ahead of the slowest reader.
 constexpr int kMaxWorld = 8;
 struct PredCand {
 	unsigned long long key;
 	ShooterRec rec;
 	int pad[2];
 };
-// Per-shot mail is self-validating: two 16-byte halves, each carrying the shot tag and written with one
-// 128-bit store, so no system-scope fence and no separate flag are needed (a half is one NVLink write).
-struct alignas(32) ShotMail {
-	uint4 h0;	// key lo, key hi, dB0 bits, tag
-	uint4 h1;	// dB1 bits, dB2 bits, tag, 0
-};
-__device__ __forceinline__ void send_mail(ShotMail *dst, const Partial &p, unsigned tag) {
-	const unsigned long long key = p.key;
-	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&dst->h0), "r"((unsigned)key), "r"((unsigned)(key >> 32)),
-		     "r"(__float_as_uint(p.dB[0])), "r"(tag) : "memory");
-	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&dst->h1), "r"(__float_as_uint(p.dB[1])),
-		     "r"(__float_as_uint(p.dB[2])), "r"(tag), "r"(0u) : "memory");
-}
-__device__ __forceinline__ bool read_mail(const ShotMail *src, unsigned tag, Partial *out) {
-	uint4 a, b;
-	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(&src->h0) : "memory");
-	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(&src->h1) : "memory");
-	if (a.w != tag || b.z != tag) return false;
-	out->key = ((unsigned long long)a.y << 32) | a.x;
-	out->dB[0] = __uint_as_float(a.z), out->dB[1] = __uint_as_float(b.x), out->dB[2] = __uint_as_float(b.y), out->pad = 0;
-	return true;
-}
-
 struct PeerBox {
-	ShotMail shot[2][kMaxWorld];
 	PredCand pred[2][kMaxWorld][kMaxRows];
 	unsigned long long pred_seq[2][kMaxWorld];
+	CandRec cand[2][kMaxRows];
+	unsigned long long cand_seq[2][kMaxWorld];
+	unsigned long long viol[2][kMaxWorld];
 };
 
 struct FastState {
 	PeerBox *box[kMaxWorld];	// box[r] = rank r's mailbox (peer-mapped); box[rank] is local
 	int rank, world;
-	unsigned long long epoch;	// run epoch (bumped by reset / rewind on every rank alike)
-	unsigned long long *pred_round;	// rounds predicted so far in this epoch (device)
+	unsigned long long *pred_round;	// (run epoch << 40) | rounds predicted so far in this epoch; the epoch is bumped by reset /
+					// rewind on every rank alike, so stale mail of an earlier run can never match (device memory: the
+					// kernel arguments stay the same from run to run, which lets a captured graph be reused)
+	unsigned long long cond;	// cudaGraphConditionalHandle of the round loop (0: rounds are launched by the host)
 	int *error;			// set when a peer wait timed out
 	unsigned long long *dbg;	// optional [16] %globaltimer stamps of predict_kernel's phases (nullptr = off)
 	float2 *ff;			// [rows][U] cached form factors: .x toward half 0, .y toward half 1
@@ -98,13 +78,16 @@ struct FastState {
 	int *ntodo;
 	unsigned long long *group_key;	// [kPredictGroups]
 	unsigned *ticket;
-	ShotRec *handoff;		// current shooter between kernels
-	Partial *partial;		// [2][max CTAs], 32-byte records
-	unsigned *barrier;		// grid barrier counter (zeroed by the last CTA of predict_kernel before each shots launch)
+	ShotRec *handoff;		// the exact argmax as predict_kernel saw it
 	long long *budget;		// shots the current radk_ctx_step call may still run
 	unsigned *row_mask;		// [rows][mask_words] bit n set <=> leaf n's list contains the row's logsrc
 	int mask_words;
-	int *stalled;			// 1: shots_kernel stopped on a cache miss
+	ShotSched *sched;		// [kMaxChain] this round's schedule (chain_kernel)
+	int *nsched;			// its length
+	int *viol;			// first violation found by this rank's receivers (nsched: none)
+	unsigned *apply_ticket;		// last-CTA-done counter of apply_kernel (multi-GPU: the last CTA mails viol)
+	float4 *st_prev[3];		// [R] the receivers' state before the round's apply pass
+	unsigned long long *counters;	// [8] 0: rows filled, 1: rounds, 2: shots scheduled, 3: shots committed, 4: rounds that re-applied
 };
 
 // Spin until *p == expected (p is in local memory, written by a peer).  Gives up after ~20 s of SM
@@ -206,7 +189,6 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence();
-	if (threadIdx.x == 0) *F.barrier = 0u;	// the round's shots_kernel counts its grid barriers from zero
 	dbg_stamp(F, 1);
 	// ---- last CTA: the `rows` largest group maxima.  Threads 0..255 own eight keys each; per round a thread
 	// maximum, an 8-warp reduction and one named barrier of 256 threads - the other 24 warps wait below.
@@ -244,17 +226,17 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	}
 	__syncthreads();
 	dbg_stamp(F, 2);
+	__shared__ unsigned long long s_round;
+	if (threadIdx.x == 0) s_round = ++(*F.pred_round);	// rounds are numbered from 1 within a run epoch
+	__syncthreads();
 	if (F.world > 1) {
 		// multi-GPU: publish the local candidates (key + complete shooter record) to every rank; the cache is
 		// rebuilt by predict_merge_kernel from the union
 		if (threadIdx.x == 0) *F.ticket = 0u;
-		__shared__ unsigned long long s_round;
-		if (threadIdx.x == 0) s_round = ++(*F.pred_round);
-		__syncthreads();
 		const int par = (int)(s_round & 1ull);
 		if (threadIdx.x < rows) {
 			PredCand pc;
-			pc.key = top[threadIdx.x], pc.pad[0] = pc.pad[1] = 0;
+			pc.key = top[threadIdx.x], pc.pad[0] = rows, pc.pad[1] = 0;	// pad[0]: every rank must run the same cache size
 			pc.rec.valid = 0;
 			// the record only travels when no rank has it yet (the caches are identical on all ranks)
 			const bool fresh = pc.key != 0ull && F.slot_row[(int)(pc.key & 0xffffffffu)] < 0;
@@ -265,6 +247,7 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 					peer_copy(dst, &pc, (int)sizeof(PredCand));
 				} else {	// key + current unshot energy (the handoff needs it if this candidate is the global best)
 					*((volatile unsigned long long *)&dst->key) = pc.key;
+					*((volatile int *)&dst->pad[0]) = rows;
 					if (pc.key != 0ull) {
 						const int r = S.slot_to_recv[(int)(pc.key & 0xffffffffu)];
 						*((volatile float *)&dst->rec.dB[0]) = S.st[0][r].w;
@@ -278,7 +261,7 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		if (threadIdx.x == 0) __threadfence_system();	// cumulative: orders the CTA's mail before the sequence numbers
 		__syncthreads();
 		if (threadIdx.x < F.world)
-			*((volatile unsigned long long *)&F.box[threadIdx.x]->pred_seq[par][F.rank]) = (F.epoch << 40) | s_round;
+			*((volatile unsigned long long *)&F.box[threadIdx.x]->pred_seq[par][F.rank]) = s_round;
 		return;
 	}
 	// ---- warp 0 rebuilds the cache around the candidates: lane j owns candidate j and row j
@@ -302,7 +285,7 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 				h.valid = 1;
 			}
 			*F.handoff = h;
-			*F.stalled = 0;
+			F.counters[0] += (unsigned long long)nt, F.counters[1]++;
 		}
 	}
 	__syncthreads();
@@ -332,7 +315,11 @@ __global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastStat
 	PeerBox *mine = F.box[F.rank];
 	if (threadIdx.x == 0) s_ok = 1;
 	__syncthreads();
-	if (threadIdx.x < F.world && !peer_wait(&mine->pred_seq[par][threadIdx.x], (F.epoch << 40) | round)) s_ok = 0;
+	if (threadIdx.x < F.world) {
+		if (!peer_wait(&mine->pred_seq[par][threadIdx.x], round)) s_ok = 0;
+		// every rank must rebuild the same cache: a rank that runs a different number of rows is an error
+		else if (*((volatile int *)&mine->pred[par][threadIdx.x][0].pad[0]) != F.rows) s_ok = 0;
+	}
 	__syncthreads();
 	if (!s_ok) {
 		if (threadIdx.x == 0) {
@@ -375,7 +362,7 @@ __global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastStat
 				h.valid = 1;
 			}
 			*F.handoff = h;
-			*F.stalled = 0;
+			F.counters[0] += (unsigned long long)nt, F.counters[1]++;
 		}
 	}
 	__syncthreads();
@@ -524,293 +511,229 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 	}
 }
 
-// ---- persistent shot loop -----------------------------------------------------------------------
-// Arrival with release semantics (publishes what the calling thread wrote before, i.e. its CTA's partial record) and
-// waiting with acquire loads: no separate MEMBAR.GPU on either side (church: 4.8 -> 4.5 us per shot).
-__device__ __forceinline__ void barrier_arrive(unsigned *counter) {
-	asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+// ---- chained shot loop ----------------------------------------------------------------------------
+// word of the per-round violation mail: run epoch (16 bits) | round (40 bits) | first violation (8 bits)
+__device__ __forceinline__ unsigned long long viol_word(unsigned long long round, int v) {	// round = epoch << 40 | round number
+	return (round << 8) | (unsigned long long)(v & 0xff);
 }
-__device__ __forceinline__ void barrier_wait(const unsigned *counter, unsigned target) {
-	unsigned v;
-	do {
-		asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-	} while (v < target);
+__device__ __forceinline__ float ff_sum(const float2 *ff, int U, int row, int u) {
+	const float2 h = __ldg(&ff[(size_t)row * U + u]);
+	return h.x + h.y;
 }
-constexpr int kShotsBlock = 512;
-
-// CalRadiosity (shade.cpp:244-259) of one receiver from cached vertex form factors.
-__device__ __forceinline__ void apply_shot(float4 &a0, float4 &a1, float4 &a2, const int4 &id, const float4 &fk,
-					   const float2 *__restrict__ ffrow, float sdB0, float sdB1, float sdB2) {
-	const float2 h0 = __ldcg(&ffrow[id.x]), h1 = __ldcg(&ffrow[id.y]), h2 = __ldcg(&ffrow[id.z]);
-	const float ff[3] = {h0.x + h0.y, h1.x + h1.y, h2.x + h2.y};
-	const float lo[3] = {fk.x * sdB0 / 3, fk.y * sdB1 / 3, fk.z * sdB2 / 3};	// shade.cpp:247-249
-	float dB[3] = {a0.w, a1.w, a2.w};
-	float4 *acc[3] = {&a0, &a1, &a2};
-#pragma unroll
-	for (int v = 0; v < 3; v++) {
-		float d;
-		d = lo[0] * ff[v]; dB[0] += d; acc[v]->x += d;
-		d = lo[1] * ff[v]; dB[1] += d; acc[v]->y += d;
-		d = lo[2] * ff[v]; dB[2] += d; acc[v]->z += d;
+struct FFRows {	// form factor (both halves) of unique vertex u in cache row `row`
+	const float2 *ff;
+	int U;
+	__host__ __device__ __forceinline__ float operator()(int row, int u) const {
+		const float2 h = ldg(&ff[(size_t)row * U + u]);
+		return h.x + h.y;
 	}
-	a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
-}
-__device__ __forceinline__ bool unsaturated(const float4 &a0, const float4 &a1, const float4 &a2) {	// rad.cpp:424-428
-	return a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
-	       a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f;
-}
+};
 
-// RPT > 0: every thread keeps the state, vertex ids and reflectance of RPT receivers in registers for
-// the whole launch (the shard fits gridDim * 512 * RPT); RPT == 0: receivers are streamed from L2/HBM
-// every shot (any shard size).
-template <int RPT>
-__global__ void __launch_bounds__(kShotsBlock, RPT == 1 ? 2 : 1) shots_kernel(DevScene S, FastState F, int max_ctas) {
-	__shared__ ShotRec cur;
-	__shared__ unsigned long long s_key[kShotsBlock / 32];
-	__shared__ float s_dB[kShotsBlock / 32][3];
-	__shared__ Partial s_best;
-	__shared__ int s_row_slot[kMaxRows];			// cache directory: slot held by each row
-	constexpr int NR = RPT > 0 ? RPT : 1;
+// One CTA of 256 threads.  Candidate i = cache row i (the slot F.row_slot[i]); warp 0 runs the chain with lane i
+// holding candidate i (the sequential restatement is chain_schedule_host in shot_core.cuh).
+__global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
+	__shared__ CandRec cm[kMaxRows];
+	__shared__ int s_owned[kMaxRows];
+	__shared__ int s_ok;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int nctas = gridDim.x;
-	// contiguous chunk of receivers per CTA
-	const int per = (S.R + nctas - 1) / nctas;
-	const int r_begin = blockIdx.x * per, r_end = min(S.R, r_begin + per);
-	if (threadIdx.x == 0) {
-		cur = *F.handoff;
-		if (cur.valid) cur.row = F.slot_row[cur.slot];
-	}
-	if (threadIdx.x < kMaxRows) s_row_slot[threadIdx.x] = threadIdx.x < F.rows ? F.row_slot[threadIdx.x] : -1;
-	// resident receivers
-	float4 ra0[NR], ra1[NR], ra2[NR], rfk[NR];
-	int4 rid[NR];
-	int rslot[NR];
-	if (RPT > 0) {
-#pragma unroll
-		for (int k = 0; k < NR; k++) {
-			const int r = r_begin + threadIdx.x + k * kShotsBlock;
-			rslot[k] = -1;
-			if (r < r_end) {
-				ra0[k] = S.st[0][r], ra1[k] = S.st[1][r], ra2[k] = S.st[2][r];
-				rid[k] = __ldg(&S.vid[r]);
-				rfk[k] = __ldg(&S.par_fk[rid[k].w]);
-				rslot[k] = __ldg(&S.slot[r]);
-			}
+	const int rows = F.rows;
+	const unsigned long long round = *F.pred_round;
+	const int par = (int)(round & 1ull);
+	if (threadIdx.x == 0) s_ok = *F.error == 0;
+	// own candidates: state, reflectance and the form factors of every filled row at their three vertices.  Three
+	// dependent round trips in all: directory -> receiver -> (state, vertex ids) -> form factors of every (candidate, row).
+	__shared__ int4 s_id[kMaxRows];
+	__shared__ int s_filled[kMaxRows];
+	if (threadIdx.x < kMaxRows) {
+		const int i = threadIdx.x;
+		const int slot = i < rows ? F.row_slot[i] : -1;
+		const int r = slot >= 0 ? S.slot_to_recv[slot] : -1;
+		s_owned[i] = r >= 0, s_filled[i] = slot >= 0;
+		cm[i].slot = r >= 0 ? slot : -1;	// free row, or a candidate owned by another rank (filled in below)
+		if (r >= 0) {
+			const int4 id = __ldg(&S.vid[r]);
+			s_id[i] = id;
+			cm[i].a0 = S.st[0][r], cm[i].a1 = S.st[1][r], cm[i].a2 = S.st[2][r];
+			const float4 fk = __ldg(&S.par_fk[id.w]);
+			cm[i].fk[0] = fk.x, cm[i].fk[1] = fk.y, cm[i].fk[2] = fk.z;
 		}
 	}
 	__syncthreads();
-	long long budget = *F.budget;
-	const long long shots_before = *S.sel.shots_done;
-	unsigned epoch = 0;
-	int parity = 0;
-	long long done = 0;
-	int stalled = 0;
-	unsigned long long tA = 0, tB = 0, tC = 0, tD = 0, tmark = 0;
-	const bool dbg = F.dbg && blockIdx.x == 0 && threadIdx.x == 0;
-	auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-	while (true) {
-		if (!cur.valid || budget <= 0) break;
-		if (cur.row < 0) { stalled = 1; break; }
-		if (dbg) tmark = now();
-		const float2 *ffrow = F.ff + (size_t)cur.row * S.U;
-		const int shooter_slot = cur.slot;
-		const float sdB0 = cur.dB[0], sdB1 = cur.dB[1], sdB2 = cur.dB[2];
-		unsigned long long key = 0ull;
-		float kd0 = 0.f, kd1 = 0.f, kd2 = 0.f;
-		if (RPT > 0) {
-#pragma unroll
-			for (int k = 0; k < NR; k++) {
-				if (rslot[k] < 0) continue;
-				if (rslot[k] == shooter_slot) ra0[k].w = ra1[k].w = ra2[k].w = 0.0f;	// rad.cpp:446-449
-				else if (unsaturated(ra0[k], ra1[k], ra2[k])) apply_shot(ra0[k], ra1[k], ra2[k], rid[k], rfk[k], ffrow, sdB0, sdB1, sdB2);
-				unsigned c;
-				const unsigned long long kk = candidate_key(S, ra0[k].w, ra1[k].w, ra2[k].w, rslot[k], ~0ull, &c);
-				if (kk > key) key = kk, kd0 = ra0[k].w, kd1 = ra1[k].w, kd2 = ra2[k].w;
-			}
-		} else {
-			// streamed receivers (HBM bound: 96 B of state + 20 B of ids per receiver and shot): kStreamUnroll receivers
-			// per thread are in flight together - all their loads are issued before the first update, the vertex
-			// ids and form-factor gathers of one overlap the state loads of the others
-			constexpr int kStreamUnroll = 4;
-			for (int r0 = r_begin + threadIdx.x; r0 < r_end; r0 += kShotsBlock * kStreamUnroll) {
-				float4 a0[kStreamUnroll], a1[kStreamUnroll], a2[kStreamUnroll], fk[kStreamUnroll];
-				int4 id[kStreamUnroll];
-				int slot[kStreamUnroll];
-#pragma unroll
-				for (int k = 0; k < kStreamUnroll; k++) {
-					const int r = r0 + k * kShotsBlock;
-					slot[k] = -1;
-					if (r < r_end) {
-						a0[k] = S.st[0][r], a1[k] = S.st[1][r], a2[k] = S.st[2][r];
-						slot[k] = __ldg(&S.slot[r]);
-						id[k] = __ldg(&S.vid[r]);
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < kStreamUnroll; k++)
-					if (slot[k] >= 0) fk[k] = __ldg(&S.par_fk[id[k].w]);
-#pragma unroll
-				for (int k = 0; k < kStreamUnroll; k++) {
-					const int r = r0 + k * kShotsBlock;
-					if (slot[k] < 0) continue;
-					if (slot[k] == shooter_slot) {
-						a0[k].w = a1[k].w = a2[k].w = 0.0f;
-						S.st[0][r].w = 0.0f, S.st[1][r].w = 0.0f, S.st[2][r].w = 0.0f;
-					} else if (unsaturated(a0[k], a1[k], a2[k])) {
-						apply_shot(a0[k], a1[k], a2[k], id[k], fk[k], ffrow, sdB0, sdB1, sdB2);
-						S.st[0][r] = a0[k], S.st[1][r] = a1[k], S.st[2][r] = a2[k];
-					}
-					unsigned c;
-					const unsigned long long kk = candidate_key(S, a0[k].w, a1[k].w, a2[k].w, slot[k], ~0ull, &c);
-					if (kk > key) key = kk, kd0 = a0[k].w, kd1 = a1[k].w, kd2 = a2[k].w;
-				}
+	for (int q = threadIdx.x; q < kMaxRows * kMaxRows; q += 256) {	// (candidate i, row j)
+		const int i = q >> 5, j = q & 31;
+		if (!s_owned[i]) continue;
+		const bool filled = s_filled[j];
+		const int4 id = s_id[i];
+		cm[i].fsum[j][0] = filled ? ff_sum(F.ff, S.U, j, id.x) : 0.0f;
+		cm[i].fsum[j][1] = filled ? ff_sum(F.ff, S.U, j, id.y) : 0.0f;
+		cm[i].fsum[j][2] = filled ? ff_sum(F.ff, S.U, j, id.z) : 0.0f;
+	}
+	__syncthreads();
+	if (F.world > 1) {
+		// publish the owned records to every other rank (4-byte granules, one warp per record), then the sequence number
+		for (int i = warp; i < rows; i += 8) {
+			if (!s_owned[i]) continue;
+			const int *src = (const int *)&cm[i];
+			for (int t = 0; t < F.world; t++) {
+				if (t == F.rank) continue;
+				volatile int *dst = (volatile int *)&F.box[t]->cand[par][i];
+				for (int w = lane; w < (int)(sizeof(CandRec) / 4); w += 32) dst[w] = src[w];
 			}
 		}
-		if (dbg) { const unsigned long long t = now(); tA += t - tmark; tmark = t; }
-		// CTA argmax carrying the winner's unshot energy
-		const unsigned long long wmax = warp_max_u64(key);
-		const unsigned src = __ffs(__ballot_sync(0xffffffffu, key == wmax && wmax != 0ull)) - 1;
-		if (wmax != 0ull) {
-			kd0 = __shfl_sync(0xffffffffu, kd0, src), kd1 = __shfl_sync(0xffffffffu, kd1, src), kd2 = __shfl_sync(0xffffffffu, kd2, src);
-		}
-		if (lane == 0) s_key[warp] = wmax, s_dB[warp][0] = kd0, s_dB[warp][1] = kd1, s_dB[warp][2] = kd2;
 		__syncthreads();
-		if (warp == 0) {
-			unsigned long long k = lane < kShotsBlock / 32 ? s_key[lane] : 0ull;
-			const unsigned long long m = warp_max_u64(k);
-			const unsigned w = __ffs(__ballot_sync(0xffffffffu, k == m)) - 1;	// some lane < 16 holds m (possibly 0)
-			if (lane == 0) {
-				Partial p;
-				p.key = m, p.dB[0] = s_dB[w][0], p.dB[1] = s_dB[w][1], p.dB[2] = s_dB[w][2], p.pad = 0;
-				s_best = p;
-				F.partial[parity * max_ctas + blockIdx.x] = p;
-				// the CTA's record is final here - arrive at the (local) grid barrier right away
-				barrier_arrive(F.barrier);
+		if (threadIdx.x == 0) __threadfence_system();	// cumulative: the CTA's records before the sequence numbers
+		__syncthreads();
+		if (threadIdx.x < F.world && threadIdx.x != F.rank)
+			*((volatile unsigned long long *)&F.box[threadIdx.x]->cand_seq[par][F.rank]) = round;
+		PeerBox *mine = F.box[F.rank];
+		if (threadIdx.x < F.world && threadIdx.x != F.rank && s_ok && !peer_wait(&mine->cand_seq[par][threadIdx.x], round)) s_ok = 0;
+		__syncthreads();
+		if (s_ok) {
+			for (int i = warp; i < rows; i += 8) {
+				if (s_owned[i] || F.row_slot[i] < 0) continue;
+				const volatile int *src = (const volatile int *)&mine->cand[par][i];
+				int *dst = (int *)&cm[i];
+				for (int w = lane; w < (int)(sizeof(CandRec) / 4); w += 32) dst[w] = src[w];
 			}
 		}
-		__syncthreads();	// s_key / s_dB are reused below
-		epoch++;
-		if (F.world == 1) {
-			// single GPU: publish the CTA's best, one grid barrier, then every CTA reduces all records the same way
-			// (identical `cur` everywhere, no second barrier).  The whole 32-byte record comes with one pair of
-			// 128-bit loads, and the winner's cache row is looked up in the shared-memory directory, so the
-			// barrier is followed by a single L2 round trip.
-			if (dbg) { const unsigned long long t = now(); tB += t - tmark; tmark = t; }
-			if (threadIdx.x == 0) barrier_wait(F.barrier, epoch * (unsigned)nctas);
-			__syncthreads();
-			if (dbg) { const unsigned long long t = now(); tC += t - tmark; tmark = t; }
-			unsigned long long k = 0ull;
-			float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-			if (threadIdx.x < nctas) {
-				const uint4 *rec = (const uint4 *)&F.partial[parity * max_ctas + threadIdx.x];
-				const uint4 a = __ldcg(rec), bb = __ldcg(rec + 1);
-				k = ((unsigned long long)a.y << 32) | a.x;
-				d0 = __uint_as_float(a.z), d1 = __uint_as_float(a.w), d2 = __uint_as_float(bb.x);
+		__syncthreads();
+	}
+	if (warp != 0) return;
+	if (!s_ok) {
+		if (lane == 0) *F.error = 1, *F.nsched = 0, *F.viol = 0;
+		return;
+	}
+	// ---- the chain: lane i replays the shots on candidate i
+	const bool valid = lane < rows && cm[lane].slot >= 0;
+	float4 a0 = cm[lane].a0, a1 = cm[lane].a1, a2 = cm[lane].a2;
+	const float fkx = cm[lane].fk[0], fky = cm[lane].fk[1], fkz = cm[lane].fk[2];
+	const int slot = valid ? cm[lane].slot : -1;
+	const long long budget = *F.budget;
+	const int kmax = (int)(budget < (long long)kMaxChain ? (budget < 0 ? 0 : budget) : (long long)kMaxChain);
+	unsigned long long key = valid ? energy_key(S.converge, a0.w, a1.w, a2.w, slot) : 0ull;
+	unsigned long long best = warp_max_u64(key);
+	int k = 0;
+	while (best != 0ull && k < kmax) {
+		const int b = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
+		const int sslot = __shfl_sync(0xffffffffu, slot, b);
+		const float sd0 = __shfl_sync(0xffffffffu, a0.w, b), sd1 = __shfl_sync(0xffffffffu, a1.w, b), sd2 = __shfl_sync(0xffffffffu, a2.w, b);
+		if (valid) {
+			if (slot == sslot) a0.w = a1.w = a2.w = 0.0f;	// rad.cpp:446-449
+			else if (unsaturated(a0, a1, a2))
+				apply_shot_ff(a0, a1, a2, fkx, fky, fkz, cm[lane].fsum[b][0], cm[lane].fsum[b][1], cm[lane].fsum[b][2], sd0, sd1, sd2);
+			key = energy_key(S.converge, a0.w, a1.w, a2.w, slot);
+		}
+		best = warp_max_u64(key);
+		if (lane == 0) {
+			ShotSched s;
+			s.slot = sslot, s.row = b, s.dB[0] = sd0, s.dB[1] = sd1, s.dB[2] = sd2, s.pad = 0, s.next_key = best;
+			F.sched[k] = s;
+		}
+		k++;
+	}
+	if (lane == 0) {
+		*F.nsched = k, *F.viol = k, *F.apply_ticket = 0u;
+		F.counters[2] += (unsigned long long)k;
+	}
+}
+
+// K3b for the whole schedule: one receiver per thread.  COMMIT = false: the apply pass (reads st, leaves the old state
+// in st_prev, writes the state after all scheduled shots, reports the first violation).  COMMIT = true: after the
+// first violation is known - re-applies the valid prefix from st_prev if the schedule went further, and does the
+// round's bookkeeping.
+constexpr int kApplyBlock = 256;
+template <bool COMMIT>
+__global__ void __launch_bounds__(kApplyBlock) apply_kernel(DevScene S, FastState F) {
+	__shared__ ShotSched sched[kMaxChain];
+	__shared__ int s_n, s_wmin[kApplyBlock / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int K = *F.nsched;
+	int n = K;
+	if (COMMIT) {
+		if (threadIdx.x == 0) {
+			int v = *((volatile int *)F.viol);
+			if (F.world > 1 && K > 0) {	// K is the same on every rank (identical chains): nobody mails an empty round
+				// first violation over all ranks: every CTA reads the ranks' mail from its own box
+				const unsigned long long round = *F.pred_round;
+				const int par = (int)(round & 1ull);
+				const PeerBox *mine = F.box[F.rank];
+				const unsigned long long want = viol_word(round, 0) >> 8;
+				for (int t = 0; t < F.world; t++) {
+					if (t == F.rank) continue;
+					const volatile unsigned long long *vp = &mine->viol[par][t];
+					const long long t0 = clock64();
+					unsigned spins = 0;
+					unsigned long long w;
+					while (((w = *vp) >> 8) != want) {
+						if ((++spins & 0xfff) == 0 && clock64() - t0 > 40000000000ll) { *F.error = 1; w = 0; break; }
+					}
+					const int vt = (int)(w & 0xffull);
+					v = vt < v ? vt : v;
+				}
+				if (*((volatile int *)F.error)) v = -1;	// a peer is gone: commit nothing
 			}
-			const unsigned long long m1 = warp_max_u64(k);
-			if (lane == 0) s_key[warp] = m1;
+			s_n = v < K ? v + 1 : K;
+		}
+		__syncthreads();
+		n = s_n;
+		if (blockIdx.x == 0) {	// bookkeeping of the round (rad.cpp:504-514: loop counter; shot log for the tests)
+			const long long before = *S.sel.shots_done;
+			for (int k = threadIdx.x; k < n; k += kApplyBlock) S.sel.shot_log[(before + k) % S.sel.shot_log_cap] = F.sched[k].slot;
 			__syncthreads();
-			const unsigned long long m = warp_max_u64(lane < kShotsBlock / 32 ? s_key[lane] : 0ull);	// every warp reduces the warp maxima
-			// the next shooter is written in place: slot and unshot energy by the thread that holds the winning record,
-			// its cache row (shared-memory directory) by warp 0 - one barrier ends the shot
-			if (m != 0ull && k == m) cur.slot = (int)(m & 0xffffffffu), cur.dB[0] = d0, cur.dB[1] = d1, cur.dB[2] = d2, cur.valid = 1;
-			if (warp == 0) {
-				const unsigned hit = __ballot_sync(0xffffffffu, m != 0ull && s_row_slot[lane] == (int)(m & 0xffffffffu));
-				if (lane == 0) {
-					if (blockIdx.x == 0) S.sel.shot_log[(shots_before + done) % S.sel.shot_log_cap] = shooter_slot;
-					cur.row = hit ? __ffs(hit) - 1 : -1;
-					if (m == 0ull) cur.slot = -1, cur.row = -1, cur.dB[0] = cur.dB[1] = cur.dB[2] = 0.0f, cur.valid = 0;
+			if (threadIdx.x == 0) {
+				*S.sel.shots_done = before + n;
+				*F.budget -= n;
+				atomicAdd(&S.stats->shots, (unsigned long long)n);
+				F.counters[3] += (unsigned long long)n;
+				if (n < K) F.counters[4]++;
+				// device-side round loop (CUDA graph while node): another round unless converged, out of budget or failed
+				if (F.cond) {
+					const bool more = n > 0 && !*S.sel.converged && *F.budget > 0 && !*((volatile int *)F.error);
+					cudaGraphSetConditional((cudaGraphConditionalHandle)F.cond, more ? 1u : 0u);
 				}
 			}
-			__syncthreads();
+		}
+		if (n >= K) return;	// the whole schedule was valid: the apply pass already wrote the right state
+	}
+	if (n <= 0) return;
+	for (int k = threadIdx.x; k < n; k += kApplyBlock) sched[k] = F.sched[k];
+	__syncthreads();
+	const int r = blockIdx.x * kApplyBlock + threadIdx.x;
+	int viol = n;
+	if (r < S.R) {
+		float4 a0, a1, a2;
+		if (COMMIT) {
+			a0 = F.st_prev[0][r], a1 = F.st_prev[1][r], a2 = F.st_prev[2][r];
 		} else {
-			// multi-GPU: CTA 0 waits for the local CTAs, reduces their partials and mails the rank's best to every
-			// rank; every CTA (on every rank) then waits for all ranks' mail in its own box.
-			const unsigned tag = (unsigned)F.epoch * 0x9E3779B1u + (unsigned)(shots_before + done + 1);	// never equals a stale slot's tag
-			if (blockIdx.x == 0) {
-				if (threadIdx.x == 0) barrier_wait(F.barrier, epoch * (unsigned)nctas);
-				__syncthreads();
-				unsigned long long k = 0ull;
-				int who = -1;
-				for (int b = threadIdx.x; b < nctas; b += kShotsBlock) {
-					const unsigned long long kb = __ldcg(&F.partial[parity * max_ctas + b].key);
-					if (kb > k) k = kb, who = b;
-				}
-				const unsigned long long m1 = warp_max_u64(k);
-				if (lane == 0) s_key[warp] = m1;
-				__syncthreads();
-				unsigned long long m = 0ull;
-				for (int w = 0; w < kShotsBlock / 32; w++) m = s_key[w] > m ? s_key[w] : m;
-				if (threadIdx.x == 0) s_best.key = 0ull, s_best.dB[0] = s_best.dB[1] = s_best.dB[2] = 0.0f, s_best.pad = 0;
-				__syncthreads();
-				if (m != 0ull && k == m) {
-					const Partial *p = &F.partial[parity * max_ctas + who];
-					s_best.key = m, s_best.dB[0] = __ldcg(&p->dB[0]), s_best.dB[1] = __ldcg(&p->dB[1]), s_best.dB[2] = __ldcg(&p->dB[2]);
-				}
-				__syncthreads();
-				if (threadIdx.x < F.world) send_mail(&F.box[threadIdx.x]->shot[parity][F.rank], s_best, tag);
-			}
-			__shared__ int s_ok;
-			if (threadIdx.x == 0) s_ok = 1;
-			__syncthreads();
-			PeerBox *mine = F.box[F.rank];
-			__shared__ Partial s_mail[kMaxWorld];
-			if (threadIdx.x < F.world) {
-				const long long t0 = clock64();
-				unsigned spins = 0;
-				while (!read_mail(&mine->shot[parity][threadIdx.x], tag, &s_mail[threadIdx.x])) {
-					if ((++spins & 0xfff) == 0 && clock64() - t0 > 40000000000ll) { s_ok = 0; break; }
-				}
-			}
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				Partial best;
-				best.key = 0ull, best.dB[0] = best.dB[1] = best.dB[2] = 0.0f, best.pad = 0;
-				if (s_ok) {
-					for (int t = 0; t < F.world; t++)
-						if (s_mail[t].key > best.key) best = s_mail[t];
-				} else {
-					*F.error = 1;
-				}
-				s_best = best;
-			}
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				if (blockIdx.x == 0) S.sel.shot_log[(shots_before + done) % S.sel.shot_log_cap] = shooter_slot;
-				ShotRec n;
-				n.pad[0] = n.pad[1] = 0;
-				if (s_best.key == 0ull) {
-					n.slot = -1, n.row = -1, n.dB[0] = n.dB[1] = n.dB[2] = 0.0f, n.valid = 0;
-				} else {
-					n.slot = (int)(s_best.key & 0xffffffffu);
-					n.row = -1;
-					for (int j = 0; j < F.rows; j++)
-						if (s_row_slot[j] == n.slot) n.row = j;
-					n.dB[0] = s_best.dB[0], n.dB[1] = s_best.dB[1], n.dB[2] = s_best.dB[2];
-					n.valid = 1;
-				}
-				cur = n;
-			}
-			__syncthreads();
+			a0 = S.st[0][r], a1 = S.st[1][r], a2 = S.st[2][r];
+			F.st_prev[0][r] = a0, F.st_prev[1][r] = a1, F.st_prev[2][r] = a2;
 		}
-		if (dbg) { const unsigned long long t = now(); tD += t - tmark; tmark = t; }
-		done++, budget--, parity ^= 1;
+		const int4 id = __ldg(&S.vid[r]);
+		const int slot = __ldg(&S.slot[r]);
+		const float4 fk = __ldg(&S.par_fk[id.w]);
+		viol = apply_schedule(a0, a1, a2, id.x, id.y, id.z, fk.x, fk.y, fk.z, slot, sched, n, S.converge, FFRows{F.ff, S.U});
+		S.st[0][r] = a0, S.st[1][r] = a1, S.st[2][r] = a2;
 	}
-	if (RPT > 0) {	// write the resident state back
-#pragma unroll
-		for (int k = 0; k < NR; k++) {
-			const int r = r_begin + threadIdx.x + k * kShotsBlock;
-			if (rslot[k] >= 0) S.st[0][r] = ra0[k], S.st[1][r] = ra1[k], S.st[2][r] = ra2[k];
+	if (COMMIT) return;
+	// first violation of this rank: CTA minimum -> atomicMin; multi-GPU: the last CTA mails the rank's value
+	const int wmin = __reduce_min_sync(0xffffffffu, viol);
+	if (lane == 0) s_wmin[warp] = wmin;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int m = n;
+		for (int w = 0; w < kApplyBlock / 32; w++) m = s_wmin[w] < m ? s_wmin[w] : m;
+		if (m < n) atomicMin(F.viol, m);
+		if (F.world > 1) {
+			__threadfence();
+			if (atomicAdd(F.apply_ticket, 1u) == gridDim.x - 1) {
+				__threadfence();
+				const int v = *((volatile int *)F.viol);
+				const unsigned long long round = *F.pred_round;
+				const unsigned long long w = viol_word(round, v);
+				for (int t = 0; t < F.world; t++)
+					if (t != F.rank) *((volatile unsigned long long *)&F.box[t]->viol[(int)(round & 1ull)][F.rank]) = w;
+			}
 		}
-	}
-	if (dbg) { F.dbg[8] += tA, F.dbg[9] += tB, F.dbg[10] += tC, F.dbg[11] += tD, F.dbg[12] += (unsigned long long)done; }
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		*F.handoff = cur;
-		*F.budget = budget;
-		*S.sel.shots_done += done;
-		atomicAdd(&S.stats->shots, (unsigned long long)done);
-		*F.stalled = stalled;
-		if (!cur.valid) *S.sel.converged = 1;
 	}
 }
 

@@ -22,6 +22,7 @@
 // Per-original tables (n, |n|, Frgb*k) and the octree stay L2/L1 resident.
 #pragma once
 #include "rt_core.cuh"
+#include "shot_core.cuh"
 
 namespace radk {
 
@@ -68,17 +69,9 @@ struct DevScene {
 };
 
 // ---- selection -------------------------------------------------------------------------------------
-// key = (order-preserving bits of delta) << 32 | slot : lexicographic max == the reference's
-// sort-ascending-take-from-the-back over pair<float,int> (rad.cpp:398-402).
-__device__ __forceinline__ unsigned ordered_bits(float f) {
-	unsigned u = __float_as_uint(f);
-	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
+// keys: shot_core.cuh (make_key / energy_key)
 __device__ __forceinline__ float unordered_bits(unsigned o) {
 	return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
-}
-__device__ __forceinline__ unsigned long long make_key(float delta, int slot) {
-	return ((unsigned long long)ordered_bits(delta) << 32) | (unsigned)slot;
 }
 
 // warp-wide maximum of 64-bit keys with two redux.sync instructions: maximum of the high words, then

@@ -104,7 +104,11 @@ typedef struct radk_stats {
 	long long splits;
 	long long kernel_launches;	/* kernels this context has launched */
 	long long ray_guard_trips;	/* walks aborted by the device iteration guard (reference would spin) */
-	long long reserved[4];
+	/* batched path (since the last create / reset / rewind): */
+	long long ff_rows_filled;	/* form-factor cache rows computed (one per predicted shooter) */
+	long long rounds;		/* predict -> form factors -> chain -> apply -> commit rounds */
+	long long shots_scheduled;	/* shots the chains scheduled; shots - of those - that were committed is `shots` */
+	long long rounds_reapplied;	/* rounds whose schedule went past the first violation (valid prefix applied again) */
 } radk_stats;
 
 void radk_default_opts(radk_opts *o);

@@ -16,6 +16,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+def _cuda_usable():
+    """One probe per session: can the product's library create anything on a CUDA device?"""
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # a plain `pytest` on a machine without a GPU must not look red: gpu-marked tests are skipped there
+    # (with -m gpu on the B200 box they run; the product itself still fails loudly without a device)
+    if _cuda_usable():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (no CPU fallback in the product)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 

@@ -258,94 +258,202 @@ extern "C" int emu_start_block_stats(const radk_scene *s, int shooter_slot, long
 	return 0;
 }
 
-// ---- stateful shard emulation for the world_size > 1 CPU tests (gloo) -------------------------------
-// Mirrors the device protocol: every rank offers its local best candidate (key + complete shooter
-// record), all ranks pick the maximum key, every rank applies that shot to its own shard.
+// ---- stateful shard emulation of the chained shot loop (fast_kernels.cuh) ------------------------------
+// One EmuShard = one rank: its receiver shard, its form-factor cache, the (replicated) cache directory.  A round is
+//   emu_shard_top       local top candidates (key + complete shooter record)            [predict_kernel]
+//   emu_shard_begin     adopt the global top list: rebuild the cache, fill the new rows  [predict_merge + ff_batch]
+//   emu_shard_cands     records of the candidates this rank owns                         [chain_kernel, first half]
+//   emu_shard_chain     schedule from the complete candidate records                     [chain_kernel]
+//   emu_shard_apply     apply pass, returns the rank's first violation                   [apply_kernel<false>]
+//   emu_shard_commit    global first violation -> valid prefix, re-apply if needed       [apply_kernel<true>]
+// The exchanges between the calls are done by the caller: gloo all_gathers in tests/test_multi_rank_cpu.py, plain
+// loops in emu_run_chain below.  The candidate records, the schedule and the per-receiver passes run the code of
+// shot_core.cuh that the kernels run.
+#include "shot_core.cuh"
+#include <algorithm>
+
 struct EmuShard {
 	FlatScene F;
 	DevTree T;
-	std::vector<float> ff0, ff1;
+	int rows = 0;
+	float converge = 1200.0f;
+	std::vector<int> row_slot;		// cache directory (identical on every rank)
+	std::vector<ShooterRec> rec;		// shooter record per row
+	std::vector<float> ff;			// [rows][U][2]
 	std::vector<unsigned> mask;
+	std::vector<float4> prev[3];
+	ShotSched sched[kMaxChain];
+	int nsched = 0;
+	long long rows_filled = 0, rounds = 0, reapplied = 0;
 };
 
-extern "C" void *emu_shard_open(const radk_scene *s, int rank, int world) {
+extern "C" void *emu_shard_open(const radk_scene *s, int rank, int world, int rows, float converge) {
 	EmuShard *e = new EmuShard();
 	if (flatten_scene(s, rank, world, e->F)) { delete e; return nullptr; }
 	e->T = e->F.host_tree(s);
-	e->ff0.resize(e->F.U), e->ff1.resize(e->F.U);
+	e->rows = rows, e->converge = converge;
+	e->row_slot.assign(rows, -1);
+	e->rec.resize(rows);
+	e->ff.assign((size_t)rows * e->F.U * 2, 0.0f);
 	e->mask.resize((e->T.nnodes + 31) / 32);
+	for (int v = 0; v < 3; v++) e->prev[v].resize(e->F.R);
 	return e;
 }
 extern "C" void emu_shard_close(void *h) { delete (EmuShard *)h; }
 extern "C" int emu_shard_sizes(void *h, int *R, int *U) { EmuShard *e = (EmuShard *)h; *R = e->F.R, *U = e->F.U; return 0; }
+extern "C" int emu_shooter_rec_bytes(void) { return (int)sizeof(ShooterRec); }
+extern "C" int emu_cand_rec_bytes(void) { return (int)sizeof(CandRec); }
 
-// local argmax: *key = 0 when this shard has no candidate; rec = the candidate's shooter record
-extern "C" int emu_shard_best(void *h, float converge, unsigned long long *key, ShooterRec *rec) {
-	EmuShard *e = (EmuShard *)h;
-	FlatScene &F = e->F;
-	unsigned long long best = 0;
-	for (int r = 0; r < F.R; r++) {
-		const float delta = F.st[0][r].w + F.st[1][r].w + F.st[2][r].w;
-		if (!(delta > converge)) continue;
-		const unsigned long long k = ((unsigned long long)ordered_bits(delta) << 32) | (unsigned)F.recv_slot[r];
-		best = k > best ? k : best;
-	}
-	*key = best;
-	memset(rec, 0, sizeof(*rec));
-	if (!best) return 0;
-	const int r = F.slot_to_recv[(int)(best & 0xffffffffu)];
+static void emu_make_rec(const FlatScene &F, int r, ShooterRec *rec) {
 	const float p[3][3] = {{F.geo[0][r].x, F.geo[0][r].y, F.geo[0][r].z}, {F.geo[1][r].x, F.geo[1][r].y, F.geo[1][r].z},
 			       {F.geo[2][r].x, F.geo[2][r].y, F.geo[2][r].z}};
 	const float4 pn = F.par_n[F.recv_parent[r]];
 	make_shooter(p, pn.x, pn.y, pn.z, pn.w, F.geo[2][r].w, F.st[0][r].w, F.st[1][r].w, F.st[2][r].w, F.recv_parent[r],
 		     F.recv_slot[r], r, rec);
+}
+
+// local top `rows` candidates, descending; keys[i] = 0 past the end
+extern "C" int emu_shard_top(void *h, unsigned long long *keys, ShooterRec *recs) {
+	EmuShard *e = (EmuShard *)h;
+	const FlatScene &F = e->F;
+	std::vector<unsigned long long> all;
+	for (int r = 0; r < F.R; r++) {
+		const unsigned long long k = energy_key(e->converge, F.st[0][r].w, F.st[1][r].w, F.st[2][r].w, F.recv_slot[r]);
+		if (k) all.push_back(k);
+	}
+	const size_t n = std::min<size_t>(all.size(), (size_t)e->rows);
+	std::partial_sort(all.begin(), all.begin() + n, all.end(), std::greater<unsigned long long>());
+	for (int i = 0; i < e->rows; i++) {
+		keys[i] = (size_t)i < n ? all[i] : 0ull;
+		memset(&recs[i], 0, sizeof(ShooterRec));
+		if (keys[i]) emu_make_rec(F, F.slot_to_recv[(int)(keys[i] & 0xffffffffu)], &recs[i]);
+	}
 	return 0;
 }
 
-extern "C" int emu_shard_apply(void *h, const ShooterRec *shp) {
+// global top list (descending keys, 0 = none) with the shooter records: rebuild the cache like rebuild_cache() does and
+// fill the new rows with this shard's form factors.  Returns the number of rows filled.
+extern "C" int emu_shard_begin(void *h, const unsigned long long *keys, const ShooterRec *recs) {
 	EmuShard *e = (EmuShard *)h;
 	FlatScene &F = e->F;
 	const DevTree &T = e->T;
-	const ShooterRec sh = *shp;
-	std::fill(e->mask.begin(), e->mask.end(), 0u);
-	for (int k = T.tri_leaf_begin[sh.logsrc]; k < T.tri_leaf_begin[sh.logsrc + 1]; k++)
-		e->mask[T.tri_leaves[k] >> 5] |= 1u << (T.tri_leaves[k] & 31);
-	for (int u = 0; u < F.U; u++) {
-		const float4 v = F.uv[u];
-		const int parent = float_as_int_hd(v.w);
-		const float4 pn = F.par_n[parent];
-		float out[2] = {0.0f, 0.0f};
-		const int nh = sh.splittable ? 2 : 1;
-		for (int hh = 0; hh < nh; hh++) {
-			const FFSample &smp = sh.splittable ? sh.half[hh] : sh.centre;
-			float dx, dy, dz;
-			bool cast;
-			const float ff = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, cast);
-			if (cast && ray_sees(T, e->mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc)) out[hh] = ff;
-		}
-		e->ff0[u] = out[0], e->ff1[u] = out[1];
+	const int rows = e->rows;
+	std::vector<int> cand_row(rows, -1);
+	std::vector<char> keep(rows, 0);
+	for (int i = 0; i < rows; i++) {
+		if (!keys[i]) continue;
+		const int slot = (int)(keys[i] & 0xffffffffu);
+		for (int j = 0; j < rows; j++)
+			if (e->row_slot[j] == slot) cand_row[i] = j, keep[j] = 1;
 	}
-	for (int r = 0; r < F.R; r++) {
-		float4 &a0 = F.st[0][r], &a1 = F.st[1][r], &a2 = F.st[2][r];
-		if (F.recv_slot[r] == sh.slot) { a0.w = a1.w = a2.w = 0.0f; continue; }
-		if (!(a0.x < 255.0f || a0.y < 255.0f || a0.z < 255.0f || a1.x < 255.0f || a1.y < 255.0f || a1.z < 255.0f ||
-		      a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f)) continue;
-		const int4 id = F.vid[r];
-		const int ids[3] = {id.x, id.y, id.z};
-		const float4 fk = F.par_fk[id.w];
-		const float lo[3] = {fk.x * sh.dB[0] / 3, fk.y * sh.dB[1] / 3, fk.z * sh.dB[2] / 3};
-		float dB[3] = {a0.w, a1.w, a2.w};
-		float4 *acc[3] = {&a0, &a1, &a2};
-		for (int v = 0; v < 3; v++) {
-			const float ff = e->ff0[ids[v]] + e->ff1[ids[v]];
-			float d;
-			d = lo[0] * ff; dB[0] += d; acc[v]->x += d;
-			d = lo[1] * ff; dB[1] += d; acc[v]->y += d;
-			d = lo[2] * ff; dB[2] += d; acc[v]->z += d;
+	for (int j = 0; j < rows; j++)
+		if (!keep[j]) e->row_slot[j] = -1;
+	std::vector<int> todo;
+	int next_free = 0;
+	for (int i = 0; i < rows; i++) {
+		if (!keys[i] || cand_row[i] >= 0) continue;
+		while (next_free < rows && e->row_slot[next_free] >= 0) next_free++;
+		if (next_free >= rows) break;
+		e->row_slot[next_free] = (int)(keys[i] & 0xffffffffu);
+		e->rec[next_free] = recs[i];
+		todo.push_back(next_free);
+	}
+	for (int row : todo) {
+		const ShooterRec &sh = e->rec[row];
+		std::fill(e->mask.begin(), e->mask.end(), 0u);
+		for (int k = T.tri_leaf_begin[sh.logsrc]; k < T.tri_leaf_begin[sh.logsrc + 1]; k++)
+			e->mask[T.tri_leaves[k] >> 5] |= 1u << (T.tri_leaves[k] & 31);
+		float *out = &e->ff[(size_t)row * F.U * 2];
+		for (int u = 0; u < F.U; u++) {
+			const float4 v = F.uv[u];
+			const int parent = float_as_int_hd(v.w);
+			const float4 pn = F.par_n[parent];
+			out[2 * u] = out[2 * u + 1] = 0.0f;
+			const int nh = sh.splittable ? 2 : 1;
+			for (int hh = 0; hh < nh; hh++) {
+				const FFSample &smp = sh.splittable ? sh.half[hh] : sh.centre;
+				float dx, dy, dz;
+				bool cast;
+				const float ff = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, cast);
+				if (cast && ray_sees(T, e->mask.data(), v.x, v.y, v.z, dx, dy, dz, parent, sh.logsrc)) out[2 * u + hh] = ff;
+			}
 		}
-		a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
+	}
+	e->rows_filled += (long long)todo.size(), e->rounds++;
+	return (int)todo.size();
+}
+
+struct EmuFF {
+	const float *ff;
+	int U;
+	float operator()(int row, int u) const { return ff[((size_t)row * U + u) * 2] + ff[((size_t)row * U + u) * 2 + 1]; }
+};
+
+// records of the candidates (rows) this rank owns; owned[i] = 0 for rows that are free or owned elsewhere
+extern "C" int emu_shard_cands(void *h, CandRec *out, int *owned) {
+	EmuShard *e = (EmuShard *)h;
+	const FlatScene &F = e->F;
+	const EmuFF ffa{e->ff.data(), F.U};
+	for (int i = 0; i < e->rows; i++) {
+		memset(&out[i], 0, sizeof(CandRec));
+		out[i].slot = -1, owned[i] = 0;
+		const int slot = e->row_slot[i];
+		const int r = slot >= 0 ? F.slot_to_recv[slot] : -1;
+		if (r < 0) continue;
+		owned[i] = 1;
+		CandRec &c = out[i];
+		c.a0 = F.st[0][r], c.a1 = F.st[1][r], c.a2 = F.st[2][r];
+		const int4 id = F.vid[r];
+		const float4 fk = F.par_fk[id.w];
+		c.fk[0] = fk.x, c.fk[1] = fk.y, c.fk[2] = fk.z, c.slot = slot;
+		for (int j = 0; j < e->rows; j++) {
+			const bool filled = e->row_slot[j] >= 0;
+			c.fsum[j][0] = filled ? ffa(j, id.x) : 0.0f, c.fsum[j][1] = filled ? ffa(j, id.y) : 0.0f, c.fsum[j][2] = filled ? ffa(j, id.z) : 0.0f;
+		}
 	}
 	return 0;
+}
+
+extern "C" int emu_shard_chain(void *h, const CandRec *cands, long long budget) {
+	EmuShard *e = (EmuShard *)h;
+	std::vector<CandRec> c(cands, cands + e->rows);
+	e->nsched = chain_schedule_host(c.data(), e->rows, e->converge, budget, e->sched);
+	return e->nsched;
+}
+
+extern "C" int emu_shard_apply(void *h) {
+	EmuShard *e = (EmuShard *)h;
+	FlatScene &F = e->F;
+	const EmuFF ffa{e->ff.data(), F.U};
+	int viol = e->nsched;
+	for (int r = 0; r < F.R; r++) {
+		for (int v = 0; v < 3; v++) e->prev[v][r] = F.st[v][r];
+		const int4 id = F.vid[r];
+		const float4 fk = F.par_fk[id.w];
+		const int v1 = apply_schedule(F.st[0][r], F.st[1][r], F.st[2][r], id.x, id.y, id.z, fk.x, fk.y, fk.z, F.recv_slot[r], e->sched,
+					      e->nsched, e->converge, ffa);
+		viol = std::min(viol, v1);
+	}
+	return viol;
+}
+
+// viol = minimum over the ranks; returns the number of committed shots and their shooter slots
+extern "C" int emu_shard_commit(void *h, int viol, int *slots) {
+	EmuShard *e = (EmuShard *)h;
+	FlatScene &F = e->F;
+	const int K = e->nsched, n = viol < K ? viol + 1 : K;
+	if (n < K) {
+		const EmuFF ffa{e->ff.data(), F.U};
+		for (int r = 0; r < F.R; r++) {
+			for (int v = 0; v < 3; v++) F.st[v][r] = e->prev[v][r];
+			const int4 id = F.vid[r];
+			const float4 fk = F.par_fk[id.w];
+			apply_schedule(F.st[0][r], F.st[1][r], F.st[2][r], id.x, id.y, id.z, fk.x, fk.y, fk.z, F.recv_slot[r], e->sched, n, e->converge, ffa);
+		}
+		e->reapplied++;
+	}
+	for (int k = 0; k < n; k++) slots[k] = e->sched[k].slot;
+	return n;
 }
 
 // owned slots and their state: slots[R], accB[R][9], deltaB[R][3]
@@ -361,4 +469,54 @@ extern "C" int emu_shard_state(void *h, int *slots, float *accB, float *deltaB) 
 	}
 	return 0;
 }
-extern "C" int emu_shooter_rec_bytes(void) { return (int)sizeof(ShooterRec); }
+
+// The whole chained loop for `world` ranks in one process: accB[trinum][3][3], deltaB[trinum][3] by slot, shooter slots.
+// counters: [0] rows filled (rank 0), [1] rounds, [2] rounds that re-applied a prefix.
+extern "C" int emu_run_chain(const radk_scene *s, float converge, int world, int rows, int shots, float *accB, float *deltaB,
+			      int *shooters, int *nshots_out, long long *counters) {
+	std::vector<EmuShard *> sh(world);
+	for (int w = 0; w < world; w++)
+		if (!(sh[w] = (EmuShard *)emu_shard_open(s, w, world, rows, converge))) return 1;
+	int done = 0;
+	std::vector<unsigned long long> keys((size_t)world * rows), top(rows);
+	std::vector<ShooterRec> recs((size_t)world * rows), toprec(rows);
+	std::vector<CandRec> cands(rows), mine(rows);
+	std::vector<int> owned(rows), slots(kMaxChain);
+	while (done < shots) {
+		for (int w = 0; w < world; w++) emu_shard_top(sh[w], &keys[(size_t)w * rows], &recs[(size_t)w * rows]);
+		std::vector<int> order((size_t)world * rows);
+		for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+		std::sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] > keys[b]; });
+		for (int i = 0; i < rows; i++) top[i] = keys[order[i]], toprec[i] = recs[order[i]];
+		if (!top[0]) break;	// converged
+		for (int w = 0; w < world; w++) emu_shard_begin(sh[w], top.data(), toprec.data());
+		for (int i = 0; i < rows; i++) memset(&cands[i], 0, sizeof(CandRec)), cands[i].slot = -1;
+		for (int w = 0; w < world; w++) {
+			emu_shard_cands(sh[w], mine.data(), owned.data());
+			for (int i = 0; i < rows; i++)
+				if (owned[i]) cands[i] = mine[i];
+		}
+		int K = 0, viol = kMaxChain + 1;
+		for (int w = 0; w < world; w++) K = emu_shard_chain(sh[w], cands.data(), shots - done);
+		for (int w = 0; w < world; w++) viol = std::min(viol, emu_shard_apply(sh[w]));
+		int n = 0;
+		for (int w = 0; w < world; w++) n = emu_shard_commit(sh[w], viol, slots.data());
+		if (K <= 0 || n <= 0) { for (auto e : sh) delete e; return 2; }	// the first scheduled shot is always valid
+		for (int k = 0; k < n; k++) shooters[done + k] = slots[k];
+		done += n;
+	}
+	for (int w = 0; w < world; w++) {
+		const FlatScene &F = sh[w]->F;
+		for (int r = 0; r < F.R; r++) {
+			const int slot = F.recv_slot[r];
+			for (int v = 0; v < 3; v++) {
+				accB[slot * 9 + v * 3 + 0] = F.st[v][r].x, accB[slot * 9 + v * 3 + 1] = F.st[v][r].y, accB[slot * 9 + v * 3 + 2] = F.st[v][r].z;
+				deltaB[slot * 3 + v] = F.st[v][r].w;
+			}
+		}
+	}
+	if (nshots_out) *nshots_out = done;
+	if (counters) counters[0] = sh[0]->rows_filled, counters[1] = sh[0]->rounds, counters[2] = sh[0]->reapplied;
+	for (auto e : sh) delete e;
+	return 0;
+}

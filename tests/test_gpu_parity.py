@@ -96,21 +96,6 @@ def test_fast_path_equals_per_shot_kernels(hr, models_dir, name, shots):
         assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
 
 
-@pytest.mark.parametrize("rpt", [0, 2, 4])
-def test_shot_loop_variants_equal_per_shot_kernels(hr, models_dir, monkeypatch, rpt):
-    """shots_kernel keeps 1, 2 or 4 receivers per thread in registers or streams them (large shards); small models only
-    take the first variant, so the others are forced here (RADK_SHOTS_RPT is read when the context is created)."""
-    m = hr.Model(str(models_dir / "church.tri"))
-    ref = hr.Context(m, per_shot_kernels=1)
-    ref.step(60)
-    monkeypatch.setenv("RADK_SHOTS_RPT", str(rpt))
-    c = hr.Context(m)
-    assert c.step(60)[0] == 60
-    assert c.shooter_log() == ref.shooter_log()
-    for x, y in zip(c.download(), ref.download()):
-        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
-
-
 def test_small_cache_and_budget_edges(hr, models_dir):
     m = hr.Model(str(models_dir / "model3s.tri"))
     ref = hr.Context(m, per_shot_kernels=1)

@@ -15,7 +15,7 @@ from conftest import ROOT, oracle_scene
 def emu():
     src = os.path.join(ROOT, "tests", "hostemu", "hostemu.cpp")
     so = os.path.join(ROOT, "tests", "hostemu", "libhostemu.so")
-    deps = [src] + [os.path.join(ROOT, "hw-radiosity_b200", "csrc", f) for f in ("rt_core.cuh", "scene_flatten.hpp")]
+    deps = [src] + [os.path.join(ROOT, "hw-radiosity_b200", "csrc", f) for f in ("rt_core.cuh", "shot_core.cuh", "scene_flatten.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                                "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "hw-radiosity_b200", "csrc"),
@@ -25,6 +25,7 @@ def emu():
     lib.emu_rays.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
     lib.emu_sees.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     lib.emu_set_mode.argtypes = [C.c_int]
+    lib.emu_run_chain.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
     return lib
 
 
@@ -135,3 +136,25 @@ def test_sharded_receivers_union_equals_single(hr, emu, models_dir):
             assert np.array_equal(accB[touched].view(np.uint32), accB1[touched].view(np.uint32))
             hit += 1
     assert hit >= 1
+
+
+@pytest.mark.parametrize("name,shots,world,rows", [("sbox", -1, 1, 32), ("sbox", 60, 2, 3), ("model3s", -1, 3, 32),
+                                                   ("blocks", -1, 2, 32), ("box", 120, 1, 32), ("church", 70, 2, 16)])
+def test_chained_shot_loop_matches_oracle(hr, po, emu, models_dir, name, shots, world, rows):
+    """The chained loop of fast_kernels.cuh (schedule on the candidate records, one apply pass per round, commit of
+    the valid prefix) emulated for `world` ranks with the code of shot_core.cuh: same shooters, same bits."""
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    sc = oracle_scene(po, m)
+    seq = sc.run(None if shots < 0 else shots)
+    n = m.trinum
+    accB, dB = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3), np.float32)
+    sh = np.zeros(max(len(seq), 1), np.int32)
+    ns = C.c_int()
+    cnt = (C.c_longlong * 8)()
+    assert emu.emu_run_chain(C.addressof(m.scene), 1200.0, world, rows, len(seq) if shots < 0 else shots, accB.ctypes.data,
+                             dB.ctypes.data, sh.ctypes.data, C.byref(ns), cnt) == 0
+    live = sc.slots["parent"] >= 0
+    assert list(sh[: ns.value]) == [s[0] for s in seq]
+    assert np.array_equal(accB[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
+    assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
+    assert cnt[1] <= max(1, ns.value)              # rounds

@@ -1,6 +1,7 @@
-"""CPU tier of the N > 1 path: two processes (gloo) each hold one receiver shard, exchange their best
-candidate (key + shooter record) every shot like the GPU ranks do through their mailboxes, and must
-reproduce the single-rank oracle bit for bit.  Runs the same device-core code via tests/hostemu."""
+"""CPU tier of the N > 1 path: several processes (gloo) each hold one receiver shard and run the chained shot loop
+of fast_kernels.cuh - per round three exchanges, exactly the mail the GPU ranks send each other: local top
+candidates, the candidates' records from their owners, the first violation of the schedule - and must reproduce
+the single-rank oracle bit for bit.  Runs the device-core code (rt_core.cuh, shot_core.cuh) via tests/hostemu."""
 import ctypes as C
 import os
 import sys
@@ -10,6 +11,8 @@ import pytest
 import torch.multiprocessing as mp
 
 from conftest import GOLDEN_DIR, ROOT
+
+ROWS = 8      # cache rows = candidates per round (small, so that rounds end on violations too)
 
 
 def _worker(rank, world, port, model_gz, shots, out_dir):
@@ -24,47 +27,70 @@ def _worker(rank, world, port, model_gz, shots, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     emu = C.CDLL(os.path.join(ROOT, "tests", "hostemu", "libhostemu.so"))
     emu.emu_shard_open.restype = C.c_void_p
-    emu.emu_shard_open.argtypes = [C.c_void_p, C.c_int, C.c_int]
-    emu.emu_shard_best.argtypes = [C.c_void_p, C.c_float, C.POINTER(C.c_ulonglong), C.c_void_p]
-    emu.emu_shard_apply.argtypes = [C.c_void_p, C.c_void_p]
+    emu.emu_shard_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
+    for f in ("emu_shard_top", "emu_shard_begin", "emu_shard_cands"):
+        getattr(emu, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    emu.emu_shard_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    emu.emu_shard_apply.argtypes = [C.c_void_p]
+    emu.emu_shard_commit.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     emu.emu_shard_state.argtypes = [C.c_void_p] * 4
     emu.emu_shard_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    nrec = emu.emu_shooter_rec_bytes()
+    nrec, ncand, rows = emu.emu_shooter_rec_bytes(), emu.emu_cand_rec_bytes(), ROWS
     with tempfile.TemporaryDirectory() as tmp:
         tri = os.path.join(tmp, "m.tri")
         with open(tri, "wb") as f:
             f.write(gzip.open(model_gz).read())
         m = hr.Model(tri)
-    h = emu.emu_shard_open(C.addressof(m.scene), rank, world)
-    log = []
-    for _ in range(shots):
-        key = C.c_ulonglong()
-        rec = C.create_string_buffer(nrec)
-        emu.emu_shard_best(h, 1200.0, C.byref(key), rec)
-        mine = torch.zeros(8 + nrec, dtype=torch.uint8)
-        mine[:8] = torch.frombuffer(bytearray(int(key.value).to_bytes(8, "little")), dtype=torch.uint8)
-        mine[8:] = torch.frombuffer(bytearray(rec.raw), dtype=torch.uint8)
-        gathered = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)                      # the per-shot exchange
-        keys = [int.from_bytes(bytes(g[:8].tolist()), "little") for g in gathered]
-        best = max(range(world), key=lambda r: keys[r])
-        if keys[best] == 0:
+    h = emu.emu_shard_open(C.addressof(m.scene), rank, world, rows, 1200.0)
+
+    def all_gather(arr):
+        mine = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy())
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return [p.numpy() for p in parts]
+
+    log, rounds = [], 0
+    while len(log) < shots:
+        # exchange 1: every rank's local top candidates, key + complete shooter record (predict mail)
+        keys, recs = np.zeros(rows, np.uint64), np.zeros(rows * nrec, np.uint8)
+        emu.emu_shard_top(h, keys.ctypes.data, recs.ctypes.data)
+        gk = np.concatenate([p.view(np.uint64) for p in all_gather(keys)])
+        gr = np.concatenate(all_gather(recs)).reshape(world * rows, nrec)
+        order = np.argsort(gk, kind="stable")[::-1][:rows]
+        top, toprec = np.ascontiguousarray(gk[order]), np.ascontiguousarray(gr[order])
+        if top[0] == 0:
             break
-        winner = C.create_string_buffer(bytes(gathered[best][8:].tolist()), nrec)
-        emu.emu_shard_apply(h, winner)
-        log.append(keys[best] & 0xffffffff)
+        emu.emu_shard_begin(h, top.ctypes.data, toprec.ctypes.data)
+        # exchange 2: the candidates' records from their owners
+        cands, owned = np.zeros(rows * ncand, np.uint8), np.zeros(rows, np.int32)
+        emu.emu_shard_cands(h, cands.ctypes.data, owned.ctypes.data)
+        gc, go = all_gather(cands), all_gather(owned)
+        merged = cands.reshape(rows, ncand).copy()
+        for r in range(world):
+            o = go[r].view(np.int32).astype(bool)
+            merged[o] = gc[r].reshape(rows, ncand)[o]
+        merged = np.ascontiguousarray(merged)
+        emu.emu_shard_chain(h, merged.ctypes.data, shots - len(log))
+        # exchange 3: the first violation of the schedule
+        viol = np.array([emu.emu_shard_apply(h)], np.int32)
+        v = min(int(p.view(np.int32)[0]) for p in all_gather(viol))
+        slots = np.zeros(64, np.int32)
+        n = emu.emu_shard_commit(h, v, slots.ctypes.data)
+        assert n > 0
+        log += list(slots[:n])
+        rounds += 1
     R, U = C.c_int(), C.c_int()
     emu.emu_shard_sizes(h, C.byref(R), C.byref(U))
     slots = np.zeros(R.value, np.int32)
     acc = np.zeros((R.value, 9), np.float32)
     dB = np.zeros((R.value, 3), np.float32)
     emu.emu_shard_state(h, slots.ctypes.data, acc.ctypes.data, dB.ctypes.data)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), slots=slots, acc=acc, dB=dB, log=np.array(log, np.int64))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), slots=slots, acc=acc, dB=dB, log=np.array(log, np.int64), rounds=rounds)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world,shots", [("sbox", 2, 25), ("model3s", 3, 15)])
+@pytest.mark.parametrize("name,world,shots", [("sbox", 2, 45), ("model3s", 3, 60)])
 def test_two_rank_gloo_exchange_matches_oracle(hr, po, models_dir, tmp_path, name, world, shots):
     from conftest import oracle_scene
     test_hostemu = __import__("test_hostemu")      # builds libhostemu.so if stale
@@ -81,6 +107,7 @@ def test_two_rank_gloo_exchange_matches_oracle(hr, po, models_dir, tmp_path, nam
     for r in range(world):
         d = np.load(tmp_path / f"rank{r}.npz")
         assert list(d["log"]) == [s[0] for s in seq]
+        assert int(d["rounds"]) < shots            # shots really were batched
         slots = d["slots"]
         seen += len(slots)
         assert np.array_equal(d["acc"].reshape(-1, 3, 3).view(np.uint32), sc.slots["accB"][slots].view(np.uint32))
