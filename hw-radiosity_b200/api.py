@@ -66,7 +66,7 @@ EXPORTS = [
     "radk_model_write", "radk_model_write_colors", "radk_model_write_wait", "radk_model_format", "radk_ctx_create", "radk_ctx_destroy", "radk_ctx_reset",
     "radk_ctx_rewind", "radk_ctx_step", "radk_ctx_select", "radk_ctx_shoot", "radk_ctx_shooter_log", "radk_ctx_trinum",
     "radk_ctx_download", "radk_ctx_download_triangles", "radk_ctx_snapshot_colors", "radk_ctx_stats",
-    "radk_ctx_device_ms", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_vertex_ff",
+    "radk_ctx_device_ms", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_ray_sees", "radk_vertex_ff",
     "radk_ctx_peer_handle", "radk_ctx_peer_connect", "radk_ctx_peer_connect_local", "radk_ctx_owned_slots",
 ]
 
@@ -74,7 +74,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(PKG_DIR, "libradk.so")
+    # RADK_LIB: another build of the same library (A/B of compile-time variants, tools/ff_variant.py); never a fallback
+    return os.environ.get("RADK_LIB") or os.path.join(PKG_DIR, "libradk.so")
 
 
 def build_library(force=False):
@@ -133,6 +134,7 @@ def load_library():
     L.radk_ctx_device_ms.argtypes = [vp]
     L.radk_ctx_device_ms.restype = C.c_double
     L.radk_ray_hitted.argtypes = [vp, vp, vp, vp, C.c_int, vp]
+    L.radk_ray_sees.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
     L.radk_ctx_peer_handle.argtypes = [vp, vp]
     L.radk_ctx_peer_connect.argtypes = [vp, vp, C.c_int]
     L.radk_ctx_peer_connect_local.argtypes = [vp, C.POINTER(vp), C.c_int]
@@ -379,6 +381,16 @@ class Context:
         v = np.ascontiguousarray(vertices, dtype=np.int32)
         out = np.empty(len(r), dtype=np.float32)
         _check(load_library().radk_vertex_ff(self._h, int(shooter), r.ctypes.data, v.ctypes.data, len(r), out.ctypes.data))
+        return out
+
+    def ray_sees(self, p, v, frm, logsrc):
+        """1 where RayHitted(p, v, from, logsrc) == logsrc, by the any-hit walk of the batched form-factor kernel."""
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3)
+        frm = np.ascontiguousarray(frm, dtype=np.int32).reshape(-1)
+        out = np.empty(len(p), dtype=np.int32)
+        _check(load_library().radk_ray_sees(self._h, p.ctypes.data, v.ctypes.data, frm.ctypes.data, int(logsrc), len(p),
+                                            out.ctypes.data))
         return out
 
     def ray_hitted(self, p, v, frm):

@@ -423,6 +423,19 @@ __global__ void ray_batch_kernel(DevTree T, const float *p, const float *v, cons
 	hit[i] = ray_walk<false>(T, p[3 * i], p[3 * i + 1], p[3 * i + 2], v[3 * i], v[3 * i + 1], v[3 * i + 2], from[i], nullptr);
 }
 
+// radk_ray_sees: leaf mask of one original (bit n <=> leaf n lists it), then the any-hit walk of the batched path
+__global__ void leaf_mask_kernel(DevTree T, int logsrc, unsigned *mask) {
+	for (int k = T.tri_leaf_begin[logsrc] + threadIdx.x; k < T.tri_leaf_begin[logsrc + 1]; k += blockDim.x) {
+		const int leaf = T.tri_leaves[k];
+		atomicOr(&mask[leaf >> 5], 1u << (leaf & 31));
+	}
+}
+__global__ void ray_sees_batch_kernel(DevTree T, const unsigned *mask, const float *p, const float *v, const int *from, int logsrc, int n, int *out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	out[i] = ray_sees(T, mask, p[3 * i], p[3 * i + 1], p[3 * i + 2], v[3 * i], v[3 * i + 1], v[3 * i + 2], from[i], logsrc) ? 1 : 0;
+}
+
 __global__ void vertex_ff_batch_kernel(DevScene S, const ShooterRec *shp, const int *recv, const int *vertex, int n, float *out) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;

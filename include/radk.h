@@ -208,6 +208,10 @@ int radk_ctx_sizes(const radk_ctx *c, int *receivers, int *unique_vertices, int 
 
 /* Batch RayHitted (raycast.cpp:335-360): n rays (p[n][3], v[n][3], from[n]) -> hit[n]. */
 int radk_ray_hitted(radk_ctx *c, const float *p, const float *v, const int *from, int n, int *hit);
+/* The question CalFF asks of RayHitted (shade.cpp:124): does the ray return `logsrc`?  sees[i] = 1 iff
+ * RayHitted(p[i], v[i], from[i], logsrc) == logsrc, answered by the walk the batched form-factor kernel runs
+ * (bounded any-hit leaf visits with the per-shooter leaf mask) instead of the nearest-hit walk of radk_ray_hitted. */
+int radk_ray_sees(radk_ctx *c, const float *p, const float *v, const int *from, int logsrc, int n, int *sees);
 /* Batch of AdaptCalFF(CalFF(..)) (shade.cpp:442-446) for n (receiver slot, vertex 0..2) pairs
  * against shooter slot `shooter`. */
 int radk_vertex_ff(radk_ctx *c, int shooter, const int *receiver, const int *vertex, int n, float *ff);

@@ -110,6 +110,35 @@ def check_synthetic(hr, po, leaves, expect_pow2):
     return st
 
 
+def test_synthetic_million_leaves_fifty_shots(hr, po):
+    """The scaling scene family at 1 M leaves, 50 shots: default (batched) path on one GPU and on two in-process ranks
+    against the oracle port - shooter sequence and every accB / deltaB bit."""
+    import threading
+    from hw_radiosity_b200 import synth
+    m = hr.Model(text=synth.room_scene(1000000, seed=1), tri_limit=3000000, max_tri=3000000)
+    sc = oracle_scene(po, m, converge=1.0)
+    seq = sc.run(50)
+    live = sc.slots["parent"] >= 0
+    fast = hr.Context(m, converge=1.0)
+    assert fast.step(50)[0] == len(seq) == 50 and fast.shooter_log() == [s[0] for s in seq]
+    acc, dB, _ = fast.download()
+    assert np.array_equal(acc[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
+    assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
+    fast.close()
+    ctxs = [hr.Context(m, opts=hr.default_opts(rank=r, world=2, converge=1.0)) for r in range(2)]
+    hr.Context.connect_local(ctxs)
+    th = [threading.Thread(target=c.step, args=(50,)) for c in ctxs]
+    [t.start() for t in th]
+    [t.join(timeout=600) for t in th]
+    assert not any(t.is_alive() for t in th), "a rank hung"
+    for c in ctxs:
+        own = c.owned_slots()
+        a2, d2, _ = c.download()
+        assert c.shooter_log() == [s[0] for s in seq]
+        assert np.array_equal(a2[own].view(np.uint32), sc.slots["accB"][own].view(np.uint32))
+        assert np.array_equal(d2[own].view(np.uint32), sc.slots["deltaB"][own].view(np.uint32))
+
+
 def test_synthetic_room(hr, po):
     st = check_synthetic(hr, po, 100000, True)
     assert st["ray_guard_trips"] == 0

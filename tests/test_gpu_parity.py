@@ -86,6 +86,61 @@ def test_fast_path_convergence_matches_golden(hr, golden, models_dir, name):
     assert d["accB_sha"] == g["accB_sha"] and d["deltaB_sha"] == g["deltaB_sha"]
 
 
+def test_room_120_shots_match_oracle(hr, po, models_dir):
+    """BASELINE config 2 (room.tri -converge 1200 -delta_ff 0.000005 = defaults): N >= 100 shots of the default
+    (batched) path against the oracle, shooter sequence and every accB / deltaB bit."""
+    m = hr.Model(str(models_dir / "room.tri"))
+    ctx = hr.Context(m)
+    assert ctx.step(120)[0] == 120
+    sc = oracle_scene(po, m)
+    seq = sc.run(120)
+    assert ctx.shooter_log() == [s[0] for s in seq]
+    assert_state_equal(ctx, sc)
+
+
+def _golden_full():
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "golden_full.json")) as f:
+        return json.load(f)["models"]
+
+
+@pytest.mark.parametrize("name", ["box", "hall", "room"])
+def test_long_runs_converge_to_the_reference(hr, models_dir, name):
+    """BASELINE configs 1 and 2 (and hall) to convergence: thousands of shots (box 6 294 with the -ffp-contract=off
+    reference, hall 9 009, room ~16.7 k; /root/reference/src/rad.cpp:491-523 is the loop) against goldens generated by
+    the UNMODIFIED reference (tests/golden/make_golden_full.py): shooter sequence, final accB / deltaB bits, .fin bytes."""
+    import hashlib
+    gold = _golden_full()
+    if name not in gold:
+        pytest.skip(f"tests/golden/golden_full.json has no entry for {name} (generate it with make_golden_full.py)")
+    g = gold[name]
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    ctx = hr.Context(m)                      # the default (batched) path
+    done, conv = ctx.step(-1)
+    assert conv and done == g["shots"]
+    assert ctx.shooter_log() == g["shooters"]
+    ctx.download_into(m)
+    d = state_digest(m.triangles)
+    assert d["accB_sha"] == g["accB_sha"] and d["deltaB_sha"] == g["deltaB_sha"]
+    assert hashlib.sha256(m.format()).hexdigest() == g["fin_sha"]        # byte-identical .fin
+
+
+@pytest.mark.parametrize("name", ["box"])
+def test_long_run_ray_counts_match_the_reference(hr, models_dir, name):
+    """The statistics path (per-shot kernels) over a whole long run: the reference-equivalent ray and visible-ray
+    totals of 6 294 shots equal the unmodified reference's RayHitted hook counts (zero visibility mismatches)."""
+    g = _golden_full()[name]
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    ctx = hr.Context(m, collect_stats=1)
+    done, conv = ctx.step(-1)
+    assert conv and done == g["shots"]
+    st = ctx.stats()
+    assert (st["rays"], st["visible"]) == (g["rays"], g["visible"])
+    assert ctx.shooter_log() == g["shooters"]
+
+
 @pytest.mark.parametrize("name,shots", [("box", 300), ("room", 150), ("hall", 60)])
 def test_fast_path_equals_per_shot_kernels(hr, models_dir, name, shots):
     m = hr.Model(str(models_dir / f"{name}.tri"))
@@ -186,6 +241,42 @@ def test_ray_batch_matches_oracle(hr, po, models_dir):
         p2 = np.array([[0, 0, 0], [1e9, 0, 0], [0, 0, 0]], np.float32) + np.float32(m.scene.G0[0])
         v2 = np.array([[0, 0, 0], [1, 0, 0], [1e-7, 1e-7, 1]], np.float32)
         assert np.array_equal(ctx.ray_hitted(p2, v2, [-1, -1, -1])[1:], sc.ray_hitted(p2, v2, [-1, -1, -1])[1:])
+
+
+def test_ray_sees_matches_oracle(hr, po, models_dir):
+    """The walk the timed path runs (ray_sees: bounded any-hit leaf visits + per-shooter leaf mask), ray by ray through
+    radk_ray_sees, against the oracle's RayHitted(...) == logsrc: rays from receiver vertices toward points of the
+    target original (mostly visible or blocked late), toward other triangles (mostly not returning logsrc), rays lying
+    IN the plane of an occluder through their origin (a1 = a2 = 0: t is NaN, raycast.cpp:283-313), zero directions."""
+    for name in ["church", "room", "blocks"]:
+        m = hr.Model(str(models_dir / f"{name}.tri"))
+        sc = oracle_scene(po, m)
+        ctx = hr.Context(m)
+        rng = np.random.default_rng(5)
+        tri = m.triangles
+        leaves = np.nonzero(tri["parent"] >= 0)[0]
+        mismatches = 0
+        for logsrc in rng.choice(np.unique(tri["parent"][leaves]), 6, replace=False):
+            kids = leaves[tri["parent"][leaves] == logsrc]
+            n = 30000
+            a = rng.choice(leaves, n)
+            p = tri["p"][a, rng.integers(0, 3, n)]
+            frm = tri["parent"][a].copy()
+            target = tri["c"][rng.choice(kids, n)]                       # a point on the target original
+            other = tri["c"][rng.choice(leaves, n)]
+            v = np.where((np.arange(n) % 3 == 0)[:, None], other - p, target - p).astype(np.float32)
+            # in-plane rays: origin = a vertex of some input triangle, direction = one of its edges (t = 0/0 against it)
+            k = 2000
+            o = rng.integers(0, m.n0, k)
+            p[:k] = tri["p"][o, 0]
+            v[:k] = tri["p"][o, 1] - tri["p"][o, 0]
+            frm[:k] = -1
+            v[k:k + 10] = 0.0
+            want = (sc.ray_hitted(p, v, frm) == logsrc).astype(np.int32)
+            got = ctx.ray_sees(p, v, frm, int(logsrc))
+            mismatches += int((got != want).sum())
+            assert want[k + 10:].sum() > 0                               # the sample does contain visible rays
+        assert mismatches == 0
 
 
 def test_select_matches_oracle(hr, po, models_dir):
