@@ -104,11 +104,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(tri_path, shots, threads):
+def cpu_reference_run(tri_path, shots, threads, build="ref_harness"):
     """The reference's own CPU implementation (oracle/_ref/ref_harness = unmodified sources, -O2
-    -ffp-contract=off -fopenmp) timed around its shot loop; falls back to the oracle port."""
+    -ffp-contract=off -fopenmp; ref_harness_shipped = the reference Makefile's own flags, /root/reference/Makefile:7)
+    timed around its shot loop; falls back to the oracle port."""
     from oracle import pyoracle as po
-    harness = po.ref_binary("ref_harness")
+    harness = po.ref_binary(build)
     if harness:
         args = [harness, "-jobs", str(threads), "-o", os.path.join(os.path.dirname(tri_path), "ref_out"), tri_path, "--json"]
         if shots is not None:
@@ -180,6 +181,99 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+
+def golden_entry(name):
+    """Committed golden of a repo model run to convergence by the UNMODIFIED reference (tests/golden/*.json)."""
+    gdir = os.path.join(ROOT, "tests", "golden")
+    try:
+        g = json.load(open(os.path.join(gdir, "golden.json")))["models"].get(name, {}).get("full")
+        if g:
+            g = dict(g, shooters=[s[0] for s in g["shooters"]])
+        else:
+            g = json.load(open(os.path.join(gdir, "golden_full.json")))["models"].get(name)
+        return g
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def parity_block(ctx, rank, world, gold, done):
+    """After an untimed run to convergence: gather accB / deltaB over the ranks and compare with the golden of the
+    unmodified reference - SHA-256 over the live slots, and the shooter sequence.  None without a golden."""
+    import hashlib
+    import numpy as np
+    from hw_radiosity_b200 import dist as rdist
+    _, _, parent = ctx.download()
+    state = rdist.gather_state(ctx, rank, world)
+    if gold is None:
+        return None
+    if rank != 0:
+        return {}
+    accB, deltaB = state
+    live = parent >= 0
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    return {"accB_sha_ok": sha(accB[live]) == gold["accB_sha"], "deltaB_sha_ok": sha(deltaB[live]) == gold["deltaB_sha"],
+            "shooters_ok": done == gold["shots"] and ctx.shooter_log() == list(gold["shooters"]),
+            "against": "tests/golden (unmodified reference, -ffp-contract=off)"}
+
+
+def extra_workload(name, rank, world, local_rank, barrier, max_over_ranks, flush):
+    """Device time of another BASELINE config at the current N (2 timed runs after 1 warm-up, L2 flushed, state rewound
+    on the device), with the parity flags of an untimed run where a golden exists."""
+    import hw_radiosity_b200 as hr
+    from hw_radiosity_b200 import dist as rdist
+    model_name, mkw, ckw, desc = WORKLOADS[name]
+    cap = -1 if name in ("box", "room") else SHOT_CAP.get(name, -1)
+    t_setup = time.perf_counter()
+    with tempfile.TemporaryDirectory() as tmp:
+        model = hr.Model(unpack_model(model_name, tmp), **mkw)
+    ctx = rdist.sharded_context(model, rank, world, local_rank, **ckw)
+    setup_s = time.perf_counter() - t_setup
+    ms = []
+    done = 0
+    for i in range(3):
+        ctx.rewind()
+        flush.fill_(i + 1)
+        import torch
+        torch.cuda.synchronize()
+        barrier()
+        before = ctx.device_ms
+        done, conv = ctx.step(cap)
+        ms.append(max_over_ranks(ctx.device_ms - before))
+    gold = golden_entry(model_name) if cap < 0 else None
+    par = parity_block(ctx, rank, world, gold, done)
+    sizes = ctx.sizes()
+    out = {"workload": desc if cap >= 0 else desc.split(",")[0].replace(" default options", "") + ", default options, to convergence", "device_ms": min(ms[1:]),
+           "shots": done, "us_per_shot": min(ms[1:]) * 1e3 / max(done, 1), "receivers_per_rank": sizes["receivers"],
+           "setup_s": round(setup_s, 2), "parity": par}
+    if gold:
+        out["reference_equivalent_rays"] = gold["rays"]
+        out["rays_per_s"] = gold["rays"] / (min(ms[1:]) * 1e-3)
+    ctx.close()
+    model.close()
+    barrier()
+    return out
+
+
+def split_workload():
+    """BASELINE config 3: blocks.tri with adaptive splitting enabled, -adapt_area 5, to convergence (one GPU)."""
+    import hw_radiosity_b200 as hr
+    with tempfile.TemporaryDirectory() as tmp:
+        m = hr.Model(unpack_model("blocks", tmp), prepartition=False, tri_limit=1000000, sample_area=-1.0)
+    best = None
+    for rep in range(3):
+        ctx = hr.Context(m, split_enabled=1, area_limit=5.0, sample_area=m.sample_area, tri_limit=1000000)
+        done, conv = ctx.step(-1)
+        st = ctx.stats()
+        rec = {"workload": "model/blocks.tri -adapt_area 5, adaptive splitting enabled, to convergence", "device_ms": ctx.device_ms,
+               "shots": done, "converged": conv, "slots": ctx.trinum, "splits": st["splits"], "rays": st["rays"],
+               "kernel_launches": st["kernel_launches"],
+               "parity": "statistical (own sampling RNG): tests/test_split.py; exact goldens without sampling"}
+        ctx.close()
+        if rep and (best is None or rec["device_ms"] < best["device_ms"]):
+            best = rec
+    return best
 
 
 # ----------------------------------------------------------------------------------------------
@@ -295,8 +389,17 @@ def run_ours(args):
         e2e_phases = {k: round(v / args.steps * 1e3, 3) for k, v in zip(("upload_ms", "loop_ms", "download_ms"), phases)}
         state_bytes = sizes["receivers"] * 48
 
+        # parity of THIS run's configuration (all N ranks, real peer mailboxes): one untimed run to convergence, state
+        # gathered over the ranks, compared with the golden of the unmodified reference
+        ctx.rewind()
+        c0 = ctx.stats()
+        pdone, _ = ctx.step(cap)
+        parity = parity_block(ctx, rank, world, golden_entry(model_name) if cap < 0 else None, pdone)
+        c1 = ctx.stats()
+        counters = {k: c1[k] - (c0[k] if k == "shots" else 0) for k in ("shots", "ff_rows_filled", "rounds", "shots_scheduled", "rounds_reapplied")}
+
         # CPU baseline on this box's host cores (rank 0, N=1 only): the unmodified reference, bounded sample
-        cpu = None
+        cpu = cpu_shipped = None
         threads = os.cpu_count() or 1
         if rank == 0 and world == 1:
             if model_name.startswith("synth:"):
@@ -304,29 +407,70 @@ def run_ours(args):
             else:
                 cpu_shots = None if args.workload in ("church", "blocks") else min(cap, 40)
                 cpu = cpu_reference_run(tri, cpu_shots, threads)
+                try:        # the same loop built with the reference Makefile's own flags (FMA contraction allowed)
+                    cpu_shipped = cpu_reference_run(tri, cpu_shots, threads, build="ref_harness_shipped")
+                except Exception:
+                    cpu_shipped = None
         barrier()
+        ctx.close()
+        model.close()
+
+        # the other BASELINE configs at this N (device time + parity flags), after the headline measurement
+        extras = {}
+        if args.workload == "church" and not args.no_extra:
+            for wl in args.extra.split(","):
+                if not wl:
+                    continue
+                t_x = time.perf_counter()
+                try:
+                    if wl == "blocks_split":
+                        extras[wl] = split_workload() if (rank == 0 and world == 1) else {"skipped": "adaptive splitting runs on one GPU"}
+                    else:
+                        extras[wl] = extra_workload(wl, rank, world, local_rank, barrier, max_over_ranks, flush)
+                except Exception as e:      # an extra never takes the headline line down
+                    extras[wl] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                extras[wl]["wall_s_total"] = round(time.perf_counter() - t_x, 1)
 
     hbm_gbs, peak_src, sm_max = measured_peaks()
     hbm_gbs *= world               # aggregate peaks of the N GPUs the job runs on
-    traffic_rec = {}               # DRAM bytes per launch of the dominant kernel, from the committed ncu capture (1 GPU)
+    kprof = {}                     # per-kernel ncu figures of the committed captures (1 GPU): issue slots, FP32 pipe, active lanes, DRAM bytes
     try:
-        traffic_rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
+        kprof = json.load(open(os.path.join(ROOT, "profiles", "r02_kernels.json"))).get(args.workload, {})
     except (OSError, ValueError):
         pass
-    # dominant kernel: the visibility / form-factor kernel (K3a: ff_batch_kernel).  Algorithmic bytes per launch =
-    # 160 B x shaded receivers of the shots whose form factors the launch produced.
+    # T_shot >= max(160 B x shaded receivers / HBM peak, counted FP32 ops / FP32 peak); roofline.frac is
+    # that bound over the MEASURED time of the whole step (every kernel of the loop, not the dominant one alone).
     ff_ms, ff_n = kt["ms"]["form_factor"], max(kt["launches"]["form_factor"], 1)
-    upd_ms = kt["ms"]["update"]
     recv_per_shot = recv_shaded / max(shots_per_step, 1)
     algo_bytes_per_step = ALGO_BYTES_PER_RECEIVER * recv_shaded
-    dom = "ff_batch_kernel (K3a: culls + form factor + octree walk)" if ff_ms >= upd_ms else "shots_kernel (K3b+K1)"
-    dom_ms = max(ff_ms, upd_ms)
-    traffic = traffic_rec.get("dram_bytes_per_launch") if world == 1 and dom.startswith(traffic_rec.get("kernel", "?")) else None
-    achieved = algo_bytes_per_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    # FP32 side of the SURVEY section 8(d) roofline, counted per traced ray by the device itself
-    flops = (35 * walk["calff"] + 12 * walk["leaf_visits"] + 6 * walk["descent_steps"] + 22 * (walk["leaf_visits"] - walk["tri_accepts"] * 0)
+    flops = (35 * walk["calff"] + 12 * walk["leaf_visits"] + 6 * walk["descent_steps"] + 22 * walk["leaf_visits"]
              + 14 * walk["tri_tests"] + 24 * walk["tri_accepts"])
     p_fp32 = 148 * 128 * 2 * sm_max * 1e6 * world
+    t_bytes, t_flops = algo_bytes_per_step / (hbm_gbs * 1e9), flops / p_fp32          # seconds per step at the two roofs
+    step_s = ms_per_step * 1e-3
+    if t_bytes >= t_flops:
+        roof = {"bound": "hbm", "achieved": algo_bytes_per_step / step_s / 1e9, "peak": hbm_gbs, "unit": "GB/s"}
+    else:
+        roof = {"bound": "fp32", "achieved": flops / step_s / 1e12, "peak": p_fp32 / 1e12, "unit": "TFLOP/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    dom = max(kt["ms"], key=lambda k: kt["ms"][k])
+    dom_name = {"form_factor": "ff_stream_kernel (K3a: culls + form factor + octree walk)", "update": "chain/apply/commit kernels (K3b)",
+                "select": "predict_kernel (K1+K2)"}[dom]
+    traffic = kprof.get(dom, {}).get("dram_bytes_per_launch") if world == 1 else None
+    roof.update({
+        "traffic": traffic, "kernel": dom_name, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
+        "definition": "SURVEY 8(d) whole-step fraction: max(160 B x shaded receivers / HBM peak, counted FP32 ops / FP32 peak) / measured device time of the step",
+        "bound_us_per_shot": max(t_bytes, t_flops) / max(shots_per_step, 1) * 1e6,
+        "measured_us_per_shot": ms_per_step * 1e3 / max(shots_per_step, 1),
+        "hbm_side": {"algorithmic_bytes_per_step": algo_bytes_per_step, "seconds_at_peak": t_bytes},
+        "fp32_side": {"flops_per_step_counted": flops, "seconds_at_peak": t_flops, "peak_tflops": p_fp32 / 1e12,
+                      "achieved_tflops": flops / step_s / 1e12},
+        "algorithmic_bytes_per_launch": algo_bytes_per_step / ff_n,
+        "kernel_ms_per_step": kt["ms"], "kernel_launches_per_step": kt["launches"], "shots_profiled": kt["shots"],
+        "kernels_ncu": kprof or None,
+        "note": "church is neither HBM nor FP32-pipe bound in practice: the walk is issue / latency bound (kernels_ncu: issue slots, "
+                "active lanes), the receiver update is a chain of small kernels; the fraction above is the north-star's definition"})
+    runs = max(counters["rounds"], 1)
     line = {
         "metric": "visibility_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -344,27 +488,24 @@ def run_ours(args):
         "clocks": clk.summary(),
         "e2e": {"value": rays_per_step / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": state_bytes,
                 "d2h_bytes_per_step": state_bytes, "seconds_per_step": e2e_s, **e2e_phases},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": traffic, "kernel": dom, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
-                     "algorithmic_bytes_per_launch": algo_bytes_per_step / ff_n,
-                     "note": "achieved = 160 B x shaded receivers of the step / summed launch time of the dominant kernel "
-                             "(CUDA events per launch, profiled run); church is FP32-issue/latency bound, not HBM bound "
-                             "(SURVEY 8d): see fp32 and shot_roofline",
-                     "kernel_ms_per_step": kt["ms"], "kernel_launches_per_step": kt["launches"], "shots_profiled": kt["shots"]},
-        "shot_roofline": {"definition": "SURVEY 8(d): T_shot >= max(160 B x active receivers / HBM peak, counted FP32 ops / FP32 peak)",
-                          "bound_us_per_shot": max(ALGO_BYTES_PER_RECEIVER * recv_per_shot / (hbm_gbs * 1e9), flops / max(shots_per_step, 1) / p_fp32) * 1e6,
-                          "measured_us_per_shot": ms_per_step * 1e3 / max(shots_per_step, 1),
-                          "frac": max(ALGO_BYTES_PER_RECEIVER * recv_per_shot / (hbm_gbs * 1e9), flops / max(shots_per_step, 1) / p_fp32) / (ms_per_step * 1e-3 / max(shots_per_step, 1))},
-        "fp32": {"flops_per_step_counted": flops, "achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
-                 "peak_tflops": p_fp32 / 1e12, "frac": flops / (ms_per_step * 1e-3) / p_fp32},
+        "roofline": roof,
+        "parity": parity,
+        "speculation": {"ff_rows_filled_per_shot": counters["ff_rows_filled"] / max(counters["shots"], 1),
+                        "shots_scheduled_per_shot_committed": counters["shots_scheduled"] / max(counters["shots"], 1),
+                        "rounds_reapplied_frac": counters["rounds_reapplied"] / runs,
+                        "note": "rows filled = form-factor rows computed; every committed shot needs one, the excess was evicted unused"},
+        "workloads": extras or None,
     }
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["rays"] / cpu["seconds"], "unit": "rays/s", "cores": threads, "kind": cpu["kind"],
                                 "sample": f"{model_name}, {cpu['shots']} shots, shot loop only ({cpu['seconds']:.2f} s)",
-                                "seconds": cpu["seconds"]}
+                                "seconds": cpu["seconds"], "build": "-O2 -ffp-contract=off (the parity oracle)"}
+        if cpu_shipped is not None:
+            line["cpu_baseline"]["shipped_flags"] = {
+                "value": cpu_shipped["rays"] / cpu_shipped["seconds"], "seconds": cpu_shipped["seconds"], "shots": cpu_shipped["shots"],
+                "build": "-O2 -march=native -msse -msse2 (reference Makefile:7; FMA contraction allowed, results differ in the last bits)"}
     if rank == 0:
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -377,6 +518,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="church", choices=sorted(WORKLOADS))
+    ap.add_argument("--extra", default="box,room,blocks_split,synth10m",
+                    help="other BASELINE configs reported in the `workloads` block of the church line (device ms + parity)")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

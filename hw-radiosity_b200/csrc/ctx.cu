@@ -112,7 +112,6 @@ struct radk_ctx {
 	FastState F{};
 	bool use_fast = false;
 	int rows = 0;
-	int ff_grid = 1;			// CTAs of the persistent form-factor kernel
 	long long *h_budget = nullptr;		// pinned
 	int max_blocks = 0;
 	int cur = 0;				// which of rec[0]/rec[1] holds the current shooter
@@ -227,14 +226,8 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	predict_kernel<<<64, 1024, 0, st>>>(c->S, F);
 	if (c->F.world > 1) { predict_merge_kernel<<<1, 256, 0, st>>>(c->S, F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-#if defined(RADK_FF_STREAM)
-	ff_stream_kernel<<<c->ff_grid, kSBlock, 0, st>>>(c->S, F);
-#elif defined(RADK_FF_WALK)
-	ff_walk_kernel<<<dim3((unsigned)std::max(1, (c->U + kFFWTile - 1) / kFFWTile), (unsigned)c->rows), kFFWBlock, 0, st>>>(c->S, F);
-#else
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
 	ff_batch_kernel<<<g, kFFBlock, 0, st>>>(c->S, F);
-#endif
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	chain_kernel<<<1, 256, 0, st>>>(c->S, F);
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
@@ -269,13 +262,7 @@ bool build_loop_graph(radk_ctx *c) {
 	std::vector<K> ks;
 	ks.push_back({(const void *)predict_kernel, dim3(64), dim3(1024)});
 	if (c->F.world > 1) ks.push_back({(const void *)predict_merge_kernel, dim3(1), dim3(256)});
-#if defined(RADK_FF_STREAM)
-	ks.push_back({(const void *)ff_stream_kernel, dim3((unsigned)c->ff_grid), dim3(kSBlock)});
-#elif defined(RADK_FF_WALK)
-	ks.push_back({(const void *)ff_walk_kernel, dim3((unsigned)std::max(1, (c->U + kFFWTile - 1) / kFFWTile), (unsigned)c->rows), dim3(kFFWBlock)});
-#else
 	ks.push_back({(const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock)});
-#endif
 	ks.push_back({(const void *)chain_kernel, dim3(1), dim3(256)});
 	ks.push_back({(const void *)apply_kernel<false>, dim3(nb), dim3(kApplyBlock)});
 	ks.push_back({(const void *)apply_kernel<true>, dim3(nb), dim3(kApplyBlock)});
@@ -537,7 +524,6 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.rec = c->row_rec.p, F.todo = c->todo.p, F.ntodo = c->fast_ints.p;
 		F.nsched = c->fast_ints.p + 1, F.viol = c->fast_ints.p + 2;
 		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.apply_ticket = c->fast_uints.p + 1;
-		F.ff_next = c->fast_uints.p + 2;
 		F.handoff = c->handoff.p, F.budget = c->budget.p;
 		F.sched = c->sched.p, F.counters = c->counters.p;
 		for (int v = 0; v < 3; v++) F.st_prev[v] = c->st_prev[v].p;
@@ -549,13 +535,6 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.dbg = nullptr;
 		if (getenv("RADK_DEBUG_PREDICT")) { CUDA_TRY(c->dbg.alloc(16)); CUDA_TRY(cudaMemsetAsync(c->dbg.p, 0, 16 * 8, st)); F.dbg = c->dbg.p; }
 		c->peers_connected = world == 1;
-		{	// persistent form-factor warps: as many CTAs as the device holds at once, but no more than the work of a full round
-			int dev_sms = 148, per_sm = 1;
-			CUDA_TRY(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device));
-			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ff_stream_kernel, kSBlock, 0));
-			const long long need = ((long long)rows * 2 * ((U + 127) & ~127) / kSGrab + kSBlock / 32 - 1) / (kSBlock / 32);
-			c->ff_grid = (int)std::max<long long>(1, std::min<long long>((long long)dev_sms * std::max(per_sm, 1), need));
-		}
 		int rc2 = reset_fast_state(c);
 		if (rc2) return rc2;
 	}

@@ -76,7 +76,6 @@ struct FastState {
 	ShooterRec *rec;		// [rows] shooter record per row
 	int *todo;			// [rows] rows to fill in the next ff_batch launch
 	int *ntodo;
-	unsigned *ff_next;		// work counter of ff_stream_kernel (candidate items handed out), zeroed with every new todo list
 	unsigned long long *group_key;	// [kPredictGroups]
 	unsigned *ticket;
 	ShotRec *handoff;		// the exact argmax as predict_kernel saw it
@@ -138,7 +137,7 @@ __device__ int rebuild_cache(const FastState &F, const unsigned long long *top, 
 		F.row_slot[row] = slot, F.slot_row[slot] = row, F.todo[rank] = row;
 	}
 	const int nt = nneed < nfree ? nneed : nfree;
-	if (lane == 0) *F.ntodo = nt, *F.ff_next = 0u;
+	if (lane == 0) *F.ntodo = nt;
 	*my_row = row;
 	return nt;
 }
@@ -509,296 +508,6 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 			if (verdict == 0) outh[2 * (size_t)u] = 0.0f;
 			u = -1;
 		}
-	}
-}
-
-// ---- batched form factors, generation-compacted walk ------------------------------------------------------
-// Same rays, same per-ray arithmetic as ff_batch_kernel; what changes is which lane walks which ray.  A ray needs 1 to
-// ~10 leaf steps (a third are decided in their first leaf), so with one ray per lane a warp runs as long as its
-// longest ray with most lanes idle (ncu: 16 of 32 lanes in the leaf step).  Here the CTA keeps its rays in a
-// shared-memory queue of 16-byte records {vertex | half, t, previous leaf, counters}; one generation = every live
-// ray takes ONE leaf step (lookup, list scan, NextPoint), the undecided ones are appended to the other queue
-// (warp-aggregated, so neighbours stay neighbours), barrier, swap.  Warps are dense again in every generation.
-// The two halves of a vertex are adjacent items: adjacent lanes start from the same point toward targets a fraction
-// of the shooter apart - same leaves, same lists (82 % of church's pairs visit the identical leaf sequence).
-#ifndef RADK_FFW_BLOCK
-#define RADK_FFW_BLOCK 256
-#endif
-#ifndef RADK_FFW_TILE
-#define RADK_FFW_TILE 512
-#endif
-constexpr int kFFWBlock = RADK_FFW_BLOCK;	// threads per CTA
-constexpr int kFFWTile = RADK_FFW_TILE;		// vertices per CTA (x 2 halves = candidate rays)
-#ifndef RADK_FFW_MINB
-#define RADK_FFW_MINB (1536 / RADK_FFW_BLOCK)
-#endif
-
-__global__ void __launch_bounds__(kFFWBlock, RADK_FFW_MINB) ff_walk_kernel(DevScene S, FastState F) {
-	const int j = blockIdx.y;
-	if (j >= *F.ntodo) return;
-	const int row = F.todo[j];
-	__shared__ ShooterRec sh;
-	__shared__ int4 queue[2][2 * kFFWTile];
-	__shared__ int qcount[2];
-	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)(F.rec + row))[threadIdx.x];
-	if (threadIdx.x < 2) qcount[threadIdx.x] = 0;
-	const unsigned *row_mask = F.row_mask + (size_t)row * F.mask_words;
-	__syncthreads();
-	float2 *out = F.ff + (size_t)row * S.U;
-	const int base = blockIdx.x * kFFWTile;
-	const int lane = threadIdx.x & 31;
-	const bool split = sh.splittable;
-	// phase 1: culls + analytic form factor of item i = 2 * vertex + half; survivors are queued
-#pragma unroll 2
-	for (int i = threadIdx.x; i < 2 * kFFWTile; i += kFFWBlock) {
-		const int u = base + (i >> 1), half = i & 1;
-		bool live = false;
-		if (u < S.U) {
-			if (!split && half) {
-				((float *)&out[u])[1] = 0.0f;	// the single centre sample is item 0 of the vertex
-			} else {
-				const FFSample *smp = split ? &sh.half[half] : &sh.centre;
-				const float4 v = __ldg(&S.uv[u]);
-				const float4 pn = __ldg(&S.par_n[__float_as_int(v.w)]);
-				float dx, dy, dz;
-				const float ff = ff_geom(*smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live);
-				((float *)&out[u])[half] = live ? ff : 0.0f;
-			}
-		}
-		const unsigned ball = __ballot_sync(0xffffffffu, live);
-		if (ball) {
-			int pos = 0;
-			if (lane == 0) pos = atomicAdd(&qcount[0], __popc(ball));
-			pos = __shfl_sync(0xffffffffu, pos, 0);
-			if (live) queue[0][pos + __popc(ball & ((1u << lane) - 1u))] = make_int4(2 * u + half, 0, -1, 0);
-		}
-	}
-	__syncthreads();
-	// phase 2: generations of one leaf step each
-	const DevTree &T = S.tree;
-	int cur_q = 0;
-	int n = qcount[0];
-	while (n > 0) {
-		const int nxt_q = cur_q ^ 1;
-		for (int i0 = 0; i0 < n; i0 += kFFWBlock) {	// uniform trip count: the warp votes below need every lane
-			const int i = i0 + threadIdx.x;
-			const bool have = i < n;
-			int4 st = make_int4(0, 0, -1, 0);
-			float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, t = 0;
-			int ban = 0, u = 0, half = 0;
-			if (have) {
-				st = queue[cur_q][i];
-				u = st.x >> 1, half = st.x & 1;
-				const FFSample *smp = split ? &sh.half[half] : &sh.centre;
-				const float4 v = __ldg(&S.uv[u]);
-				px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
-				vx = smp->cx - px, vy = smp->cy - py, vz = smp->cz - pz;
-				t = __int_as_float(st.y);
-			}
-			int prev = st.z;
-			unsigned sg = (unsigned)st.w;	// leaf lookups so far | "precision exceeded" retries << 11
-			int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
-			int cur = -1;
-			bool visit = false;
-			if (have) {	// phase A: leaf lookup
-				if ((sg & 0x7ffu) == 0) cur = __ldg(&S.uv_leaf[u]);	// the first probe point is the vertex itself: its leaf is static
-				else cur = leaf_of<false>(T, px + t * vx, py + t * vy, pz + t * vz, nullptr);
-				sg++;
-				if (cur < 0 || (sg & 0x7ffu) > (unsigned)kMaxWalkSteps) {
-					verdict = 0;
-				} else if (prev == cur) {		// raycast.cpp:344-351
-					t = (float)((double)t + 1.0);
-					sg += 1u << 11;
-					if ((sg >> 11) > 100000u) verdict = 0;
-				} else {
-					visit = true;
-				}
-			}
-			__syncwarp();
-			if (visit)	// phase B: the leaf's list
-				verdict = leaf_visit(T, cur, (__ldg(&row_mask[cur >> 5]) >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, sh.logsrc);
-			__syncwarp();
-			if (visit && verdict < 0) {	// phase C: NextPoint (raycast.cpp:235-251)
-				const float4 lo = leaf_lo(T, cur);
-				const float4 hi = leaf_hi(T, cur);
-				prev = cur;
-				float tn = 1000000.0f, s;
-				if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
-				if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
-				if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
-				t = (float)((double)tn + 0.1);
-			}
-			// phase D: a blocked ray zeroes the form factor phase 1 stored; an undecided one goes to the next generation
-			if (have && verdict == 0) ((float *)&out[u])[half] = 0.0f;
-			const bool again = have && verdict < 0;
-			const unsigned ball = __ballot_sync(0xffffffffu, again);
-			if (ball) {
-				int pos = 0;
-				if (lane == 0) pos = atomicAdd(&qcount[nxt_q], __popc(ball));
-				pos = __shfl_sync(0xffffffffu, pos, 0);
-				if (again) queue[nxt_q][pos + __popc(ball & ((1u << lane) - 1u))] = make_int4(st.x, __float_as_int(t), prev, (int)sg);
-			}
-		}
-		__syncthreads();
-		n = qcount[nxt_q];
-		if (threadIdx.x == 0) qcount[cur_q] = 0;	// the queue just consumed becomes the append queue of the next generation
-		__syncthreads();
-		cur_q = nxt_q;
-	}
-}
-
-// ---- batched form factors, persistent warps with private ray queues -------------------------------------------
-// Third organisation of the same rays (same arithmetic): no CTA-wide barriers at all.  Every warp owns a queue of
-// kSQ ray records {row | vertex | half, t, previous leaf | leaf lookups} in shared memory.  It grabs 256 candidate
-// items (= 128 consecutive vertices x 2 halves of one new cache row) at a time from a global counter, runs the culls
-// and the analytic form factor on 32 of them whenever the queue has room (survivors are appended), and then gives
-// every queued ray ONE leaf step, 32 rays at a time, compacting the undecided ones in place behind the write
-// pointer.  Only full groups of 32 are processed while more candidates can be fetched, so the leaf step runs with
-// all lanes until the very end of the launch (ff_batch_kernel: 16 of 32; a ray needs 1 to ~10 steps).
-#ifndef RADK_FFS_Q
-#define RADK_FFS_Q 128
-#endif
-constexpr int kSQ = RADK_FFS_Q;		// queue capacity per warp (rays)
-constexpr int kSBlock = 128;		// threads per CTA
-constexpr int kSGrab = 256;		// candidate items fetched from the global counter at a time
-constexpr int kSRowBits = 27;		// queue item word: row index << 27 | vertex << 1 | half
-
-#ifndef RADK_FFS_MINB
-#define RADK_FFS_MINB (1536 / 128)
-#endif
-__global__ void __launch_bounds__(kSBlock, RADK_FFS_MINB) ff_stream_kernel(DevScene S, FastState F) {
-	const int ntodo = *F.ntodo;
-	if (ntodo <= 0) return;
-	__shared__ int q_item[kSBlock / 32][kSQ];
-	__shared__ float q_t[kSBlock / 32][kSQ];
-	__shared__ unsigned q_ps[kSBlock / 32][kSQ];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int *qi = q_item[warp];
-	float *qt = q_t[warp];
-	unsigned *qp = q_ps[warp];
-	const DevTree &T = S.tree;
-	const unsigned row_items = 2u * (unsigned)((S.U + 127) & ~127);	// candidate items per row, a multiple of kSGrab
-	const unsigned total = row_items * (unsigned)ntodo;
-	unsigned next = 0, end = 0;	// the warp's current range of candidate items
-	bool more = true;		// the global counter may still have work
-	int count = 0;
-	for (;;) {
-		// ---- refill: culls + analytic form factor of 32 candidates at a time while the queue has room
-		while (count <= kSQ - 32) {
-			if (next >= end) {
-				if (!more) break;
-				unsigned g = 0;
-				if (lane == 0) g = atomicAdd(F.ff_next, (unsigned)kSGrab);
-				g = __shfl_sync(0xffffffffu, g, 0);
-				if (g >= total) { more = false; break; }
-				next = g, end = g + kSGrab;
-			}
-			const unsigned it = next + lane;
-			next += 32;
-			const int j = (int)(it / row_items);
-			const unsigned w = it - (unsigned)j * row_items;
-			const int u = (int)(w >> 1), half = (int)(w & 1u);
-			const int row = __ldg(&F.todo[j]);
-			bool live = false;
-			if (u < S.U) {
-				const ShooterRec *sh = F.rec + row;
-				float *o = (float *)(F.ff + (size_t)row * S.U + u) + half;
-				if (!__ldg(&sh->splittable) && half) {
-					*o = 0.0f;	// the single centre sample is item 0 of the vertex
-				} else {
-					const FFSample *smp = __ldg(&sh->splittable) ? &sh->half[half] : &sh->centre;
-					FFSample sm;
-					sm.cx = __ldg(&smp->cx), sm.cy = __ldg(&smp->cy), sm.cz = __ldg(&smp->cz);
-					sm.nx = __ldg(&smp->nx), sm.ny = __ldg(&smp->ny), sm.nz = __ldg(&smp->nz);
-					sm.area = __ldg(&smp->area), sm.nlen = __ldg(&smp->nlen);
-					const float4 v = __ldg(&S.uv[u]);
-					const float4 pn = __ldg(&S.par_n[__float_as_int(v.w)]);
-					float dx, dy, dz;
-					const float ff = ff_geom(sm, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live);
-					*o = live ? ff : 0.0f;
-				}
-			}
-			const unsigned ball = __ballot_sync(0xffffffffu, live);
-			if (live) {
-				const int pos = count + __popc(ball & ((1u << lane) - 1u));
-				qi[pos] = (j << kSRowBits) | (int)w, qt[pos] = 0.0f, qp[pos] = 0x1fffffu << 11;	// previous leaf: none
-			}
-			count += __popc(ball);
-		}
-		__syncwarp();
-		if (count == 0) break;
-		// ---- one leaf step for the queued rays: full groups only while more candidates can still arrive
-		const bool draining = !more && next >= end;
-		const int nproc = draining ? count : (count & ~31);
-		int wr = 0;
-		for (int r0 = 0; r0 < nproc; r0 += 32) {
-			const bool have = r0 + lane < nproc;
-			int item = 0;
-			float t = 0.f;
-			unsigned ps = 0;
-			if (have) item = qi[r0 + lane], t = qt[r0 + lane], ps = qp[r0 + lane];
-			const int j = item >> kSRowBits, u = (item & ((1 << kSRowBits) - 1)) >> 1, half = item & 1;
-			int row = 0, logsrc = 0, ban = 0;
-			float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
-			if (have) {
-				row = __ldg(&F.todo[j]);
-				const ShooterRec *sh = F.rec + row;
-				const FFSample *smp = __ldg(&sh->splittable) ? &sh->half[half] : &sh->centre;
-				logsrc = __ldg(&sh->logsrc);
-				const float4 v = __ldg(&S.uv[u]);
-				px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
-				vx = __ldg(&smp->cx) - px, vy = __ldg(&smp->cy) - py, vz = __ldg(&smp->cz) - pz;
-			}
-			int prev = (int)(ps >> 11);
-			unsigned steps = ps & 0x7ffu;
-			int verdict = -1;	// -1 undecided, 0 blocked / left the scene, 1 shooter visible
-			int cur = -1;
-			if (have) {	// phase A: leaf lookup (RayHitted's loop head, raycast.cpp:341-351)
-				if (steps == 0) cur = __ldg(&S.uv_leaf[u]);	// the first probe point is the vertex itself: its leaf is static
-				else cur = leaf_of<false>(T, px + t * vx, py + t * vy, pz + t * vz, nullptr);
-				steps++;
-				while (cur >= 0 && steps <= (unsigned)kMaxWalkSteps && cur == prev) {	// "Precision Exceeded": retry one unit further
-					t = (float)((double)t + 1.0);
-					cur = leaf_of<false>(T, px + t * vx, py + t * vy, pz + t * vz, nullptr);
-					steps++;
-				}
-				if (cur < 0 || steps > (unsigned)kMaxWalkSteps) verdict = 0;
-			}
-			const bool visit = have && verdict < 0;
-			__syncwarp();
-			if (visit)	// phase B: the leaf's list
-				verdict = leaf_visit(T, cur, (__ldg(&F.row_mask[(size_t)row * F.mask_words + (cur >> 5)]) >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
-			__syncwarp();
-			if (visit && verdict < 0) {	// phase C: NextPoint (raycast.cpp:235-251)
-				const float4 lo = leaf_lo(T, cur);
-				const float4 hi = leaf_hi(T, cur);
-				prev = cur;
-				float tn = 1000000.0f, s;
-				if (fabsf(vx) > 1e-6f) { s = ((vx > 0 ? hi.x : lo.x) - px) / vx; tn = (s < tn) ? s : tn; }
-				if (fabsf(vy) > 1e-6f) { s = ((vy > 0 ? hi.y : lo.y) - py) / vy; tn = (s < tn) ? s : tn; }
-				if (fabsf(vz) > 1e-6f) { s = ((vz > 0 ? hi.z : lo.z) - pz) / vz; tn = (s < tn) ? s : tn; }
-				t = (float)((double)tn + 0.1);
-			}
-			// phase D: a blocked ray zeroes the form factor the refill stored; an undecided one stays queued
-			if (have && verdict == 0) *((float *)(F.ff + (size_t)row * S.U + u) + half) = 0.0f;
-			const bool again = have && verdict < 0;
-			const unsigned ball = __ballot_sync(0xffffffffu, again);	// (also orders this group's queue reads before its writes)
-			if (again) {
-				const int pos = wr + __popc(ball & ((1u << lane) - 1u));
-				qi[pos] = item, qt[pos] = t, qp[pos] = ((unsigned)prev << 11) | steps;
-			}
-			wr += __popc(ball);
-		}
-		// the unprocessed remainder (fewer than 32 rays) moves up behind the survivors
-		const int rest = count - nproc;
-		int item = 0;
-		float t = 0.f;
-		unsigned ps = 0;
-		if (lane < rest) item = qi[nproc + lane], t = qt[nproc + lane], ps = qp[nproc + lane];
-		__syncwarp();
-		if (lane < rest) qi[wr + lane] = item, qt[wr + lane] = t, qp[wr + lane] = ps;
-		__syncwarp();
-		count = wr + rest;
 	}
 }
 

@@ -21,3 +21,7 @@ for i in range(runs):
     st = ctx.stats()
     print(f"run {i}: {done} shots conv={conv} {ctx.device_ms - t0:.3f} ms rounds={st['rounds']} rows={st['ff_rows_filled']} "
           f"scheduled={st['shots_scheduled']} reapplied={st['rounds_reapplied']}", flush=True)
+import hashlib
+import numpy as np
+accB, deltaB, parent = ctx.download()
+print("digest", hashlib.sha256(np.ascontiguousarray(accB[parent >= 0]).tobytes()).hexdigest()[:12], "log tail", ctx.shooter_log()[-5:], flush=True)
