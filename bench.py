@@ -198,20 +198,19 @@ def golden_entry(name):
         return None
 
 
-def parity_block(ctx, rank, world, gold, done):
+def parity_block(ctx, model, rank, world, gold, done):
     """After an untimed run to convergence: gather accB / deltaB over the ranks and compare with the golden of the
     unmodified reference - SHA-256 over the live slots, and the shooter sequence.  None without a golden."""
     import hashlib
     import numpy as np
     from hw_radiosity_b200 import dist as rdist
-    _, _, parent = ctx.download()
     state = rdist.gather_state(ctx, rank, world)
     if gold is None:
         return None
     if rank != 0:
         return {}
     accB, deltaB = state
-    live = parent >= 0
+    live = model.triangles["parent"] >= 0        # the frozen mesh's receivers, in slot order (the order the goldens hash)
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
     return {"accB_sha_ok": sha(accB[live]) == gold["accB_sha"], "deltaB_sha_ok": sha(deltaB[live]) == gold["deltaB_sha"],
             "shooters_ok": done == gold["shots"] and ctx.shooter_log() == list(gold["shooters"]),
@@ -242,7 +241,7 @@ def extra_workload(name, rank, world, local_rank, barrier, max_over_ranks, flush
         done, conv = ctx.step(cap)
         ms.append(max_over_ranks(ctx.device_ms - before))
     gold = golden_entry(model_name) if cap < 0 else None
-    par = parity_block(ctx, rank, world, gold, done)
+    par = parity_block(ctx, model, rank, world, gold, done)
     sizes = ctx.sizes()
     out = {"workload": desc if cap >= 0 else desc.split(",")[0].replace(" default options", "") + ", default options, to convergence", "device_ms": min(ms[1:]),
            "shots": done, "us_per_shot": min(ms[1:]) * 1e3 / max(done, 1), "receivers_per_rank": sizes["receivers"],
@@ -394,7 +393,7 @@ def run_ours(args):
         ctx.rewind()
         c0 = ctx.stats()
         pdone, _ = ctx.step(cap)
-        parity = parity_block(ctx, rank, world, golden_entry(model_name) if cap < 0 else None, pdone)
+        parity = parity_block(ctx, model, rank, world, golden_entry(model_name) if cap < 0 else None, pdone)
         c1 = ctx.stats()
         counters = {k: c1[k] - (c0[k] if k == "shots" else 0) for k in ("shots", "ff_rows_filled", "rounds", "shots_scheduled", "rounds_reapplied")}
 

@@ -224,12 +224,12 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	F.cond = 0;	// host-launched rounds: no graph condition to set
 	if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
 	predict_kernel<<<64, 1024, 0, st>>>(c->S, F);
-	if (c->F.world > 1) { predict_merge_kernel<<<1, 256, 0, st>>>(c->S, F); c->launches++; }
+	if (c->F.world > 1) { predict_merge_kernel<<<1, 1024, 0, st>>>(c->S, F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
 	ff_batch_kernel<<<g, kFFBlock, 0, st>>>(c->S, F);
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-	chain_kernel<<<1, 256, 0, st>>>(c->S, F);
+	chain_kernel<<<1, 256, chain_smem_bytes(c->rows), st>>>(c->S, F);
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
 	apply_kernel<false><<<nb, kApplyBlock, 0, st>>>(c->S, F);
 	apply_kernel<true><<<nb, kApplyBlock, 0, st>>>(c->S, F);
@@ -257,21 +257,21 @@ bool build_loop_graph(radk_ctx *c) {
 	cudaGraph_t body = cp.conditional.phGraph_out[0];
 	c->F.cond = (unsigned long long)h;
 	void *args[] = {(void *)&c->S, (void *)&c->F};
-	struct K { const void *fn; dim3 grid, block; };
+	struct K { const void *fn; dim3 grid, block; size_t smem; };
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
 	std::vector<K> ks;
-	ks.push_back({(const void *)predict_kernel, dim3(64), dim3(1024)});
-	if (c->F.world > 1) ks.push_back({(const void *)predict_merge_kernel, dim3(1), dim3(256)});
-	ks.push_back({(const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock)});
-	ks.push_back({(const void *)chain_kernel, dim3(1), dim3(256)});
-	ks.push_back({(const void *)apply_kernel<false>, dim3(nb), dim3(kApplyBlock)});
-	ks.push_back({(const void *)apply_kernel<true>, dim3(nb), dim3(kApplyBlock)});
+	ks.push_back({(const void *)predict_kernel, dim3(64), dim3(1024), 0});
+	if (c->F.world > 1) ks.push_back({(const void *)predict_merge_kernel, dim3(1), dim3(1024), 0});
+	ks.push_back({(const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock), 0});
+	ks.push_back({(const void *)chain_kernel, dim3(1), dim3(256), chain_smem_bytes(c->rows)});
+	ks.push_back({(const void *)apply_kernel<false>, dim3(nb), dim3(kApplyBlock), 0});
+	ks.push_back({(const void *)apply_kernel<true>, dim3(nb), dim3(kApplyBlock), 0});
 	cudaGraphNode_t prev = nullptr;
 	bool ok = true;
 	for (auto &k : ks) {
 		cudaKernelNodeParams kp;
 		memset(&kp, 0, sizeof(kp));
-		kp.func = (void *)k.fn, kp.gridDim = k.grid, kp.blockDim = k.block, kp.sharedMemBytes = 0, kp.kernelParams = args, kp.extra = nullptr;
+		kp.func = (void *)k.fn, kp.gridDim = k.grid, kp.blockDim = k.block, kp.sharedMemBytes = (unsigned)k.smem, kp.kernelParams = args, kp.extra = nullptr;
 		cudaGraphNode_t n;
 		if (cudaGraphAddKernelNode(&n, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp) != cudaSuccess) { ok = false; break; }
 		prev = n;
@@ -494,12 +494,21 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	c->use_fast = c->use_dedup && !o.collect_stats && !o.per_shot_kernels;
 	if (world > kMaxWorld) { set_error("world larger than 8"); return RADK_ERR_ARG; }
 	if (c->use_fast) {
-		// form-factor cache rows: 32 unless that would take more than a quarter of the free memory
+		// form-factor cache rows = candidates per round (at most kMaxRows = 128), less if the cache would take more than a
+		// quarter of the free memory (RADK_FF_ROWS / opts.ff_rows: experiments and tests; every rank of a sharded run must
+		// use the same value, which the candidate mail checks)
 		size_t free_b = 0, total_b = 0;
 		CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-		int rows = o.ff_rows > 0 ? std::min(o.ff_rows, kMaxRows) : 32;
+		// Default: 32 candidates per round; 64 when a rank holds fewer than 50 000 receivers - small shards (church on 4 / 8
+		// GPUs) are bound by the per-round latency chain and by form-factor launches too small to fill the device, large ones
+		// by the work speculation wastes when long schedules are cut short (measured, profiles/README.md round 2).  The
+		// rule only uses numbers every rank agrees on.
+		const char *env_rows = getenv("RADK_FF_ROWS");
+		const int def_rows = F.leaves_total / world < 50000 ? 64 : 32;
+		int rows = o.ff_rows > 0 ? std::min(o.ff_rows, kMaxRows) : (env_rows && atoi(env_rows) > 0 ? std::min(atoi(env_rows), kMaxRows) : def_rows);
 		while (rows > 2 && (size_t)rows * std::max(U, 1) * sizeof(float2) > free_b / 4) rows >>= 1;
 		c->rows = rows;
+		CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes(kMaxRows)));
 		CUDA_TRY(c->ffcache.alloc((size_t)rows * std::max(U, 1)));
 		CUDA_TRY(c->row_slot.alloc(kMaxRows));
 		CUDA_TRY(c->slot_row.alloc(std::max(s->trinum, 1)));
@@ -572,6 +581,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 	S.sel.shots_done = c->shots_done.p;
 	S.sel.shot_log = c->shot_log.p, S.sel.shot_log_cap = kShotLogCap;
 	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
 	c->have_current = false;
 	c->cur = 0;
 	return RADK_OK;

@@ -22,6 +22,7 @@
 // selection rule; prediction only decides which form factors are ready and which shots can be batched,
 // never which patch shoots.
 #pragma once
+#include <cstddef>
 #include <cooperative_groups.h>
 
 #include "shoot_kernels.cuh"
@@ -108,38 +109,75 @@ __device__ __forceinline__ void peer_copy(void *dst, const void *src, int bytes)
 	for (int i = 0; i < bytes / 8; i++) d[i] = q[i];
 }
 
-// Warp 0 of one CTA: rebuild the form-factor cache around the candidate keys top[0..rows) (descending,
-// 0 = none): rows whose slot is no longer a candidate are freed, candidates without a row get the free
-// rows in order; F.todo / *F.ntodo list the rows to fill.  Returns (in every lane) the number of new rows;
-// lane j's row is written to *my_row.
-__device__ int rebuild_cache(const FastState &F, const unsigned long long *top, int lane, int *my_row) {
-	const int rows = F.rows;
-	const unsigned long long key = lane < rows ? top[lane] : 0ull;
+// All threads of one CTA (>= kMaxRows of them): rebuild the form-factor cache around the candidate keys top[0..rows)
+// (descending, 0 = none; shared memory): rows whose slot is no longer a candidate are freed, candidates without a row
+// get the free rows in ascending order; F.todo / *F.ntodo list the rows to fill.  Thread j < rows owns candidate j and
+// row j.  Returns (in every thread) the number of new rows; s_row[j] = row of candidate j (-1 none), s_todo_cand[t] =
+// candidate that todo entry t serves.  Deterministic in (top, cache directory): every rank of a sharded run rebuilds
+// the same cache.
+struct CacheScratch {
+	unsigned keep[kMaxRows / 32];
+	int fcnt[kMaxRows / 32], ncnt[kMaxRows / 32];
+	int freelist[kMaxRows];
+	int row[kMaxRows];
+	int todo_cand[kMaxRows];
+	int nt;
+};
+__device__ int rebuild_cache(const FastState &F, const unsigned long long *top, CacheScratch &cs) {
+	const int rows = F.rows, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid < kMaxRows / 32) cs.keep[tid] = 0u;
+	__syncthreads();
+	const unsigned long long key = tid < rows ? top[tid] : 0ull;
 	const bool valid = key != 0ull;
 	const int slot = (int)(key & 0xffffffffu);
 	int row = valid ? F.slot_row[slot] : -1;
-	unsigned keepmask = 0u;
-	for (int j = 0; j < 32; j++) {
-		const int rj = __shfl_sync(0xffffffffu, row, j);
-		if (rj >= 0) keepmask |= 1u << rj;
+	if (row >= 0) atomicOr(&cs.keep[row >> 5], 1u << (row & 31));
+	__syncthreads();
+	int held = tid < rows ? F.row_slot[tid] : 0;		// slot held by row `tid`
+	if (tid < rows && held >= 0 && !((cs.keep[tid >> 5] >> (tid & 31)) & 1u)) {
+		F.slot_row[held] = -1, F.row_slot[tid] = -1, held = -1;
 	}
-	int held = lane < rows ? F.row_slot[lane] : 0;		// slot held by row `lane`
-	if (lane < rows && held >= 0 && !((keepmask >> lane) & 1u)) {
-		F.slot_row[held] = -1, F.row_slot[lane] = -1, held = -1;
-	}
-	const unsigned freemask = __ballot_sync(0xffffffffu, lane < rows && held < 0);
+	const bool isfree = tid < rows && held < 0;
 	const bool need = valid && row < 0;
-	const unsigned needmask = __ballot_sync(0xffffffffu, need);
-	const int rank = __popc(needmask & ((1u << lane) - 1u));
-	const int nfree = __popc(freemask), nneed = __popc(needmask);
-	if (need && rank < nfree) {
-		row = (int)__fns(freemask, 0, rank + 1);
-		F.row_slot[row] = slot, F.slot_row[slot] = row, F.todo[rank] = row;
+	const unsigned fb = __ballot_sync(0xffffffffu, isfree), nb = __ballot_sync(0xffffffffu, need);
+	if (lane == 0 && warp < kMaxRows / 32) cs.fcnt[warp] = __popc(fb), cs.ncnt[warp] = __popc(nb);
+	__syncthreads();
+	int foff = 0, noff = 0, nfree = 0, nneed = 0;
+#pragma unroll
+	for (int w = 0; w < kMaxRows / 32; w++) {
+		if (w < warp) foff += cs.fcnt[w], noff += cs.ncnt[w];
+		nfree += cs.fcnt[w], nneed += cs.ncnt[w];
+	}
+	if (isfree) cs.freelist[foff + __popc(fb & ((1u << lane) - 1u))] = tid;
+	__syncthreads();
+	if (need) {
+		const int r = noff + __popc(nb & ((1u << lane) - 1u));
+		if (r < nfree) {
+			row = cs.freelist[r];
+			F.row_slot[row] = slot, F.slot_row[slot] = row, F.todo[r] = row;
+			cs.todo_cand[r] = tid;
+		}
 	}
 	const int nt = nneed < nfree ? nneed : nfree;
-	if (lane == 0) *F.ntodo = nt;
-	*my_row = row;
+	if (tid == 0) *F.ntodo = nt, cs.nt = nt;
+	if (tid < kMaxRows) cs.row[tid] = row;
+	__syncthreads();
 	return nt;
+}
+
+// Descending bitonic sort of n = 2^k 64-bit keys in shared memory by the whole CTA (n / 2 <= blockDim.x).
+__device__ void sort_keys_desc(unsigned long long *keys, int n) {
+	for (int k = 2; k <= n; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			const int t = threadIdx.x;
+			if (t < n / 2) {
+				const int i = (t / j) * 2 * j + (t % j), p = i + j;
+				const unsigned long long a = keys[i], b = keys[p];
+				const bool desc = (i & k) == 0;	// blocks alternate direction; the last merge (k = n) is all descending
+				if (desc ? a < b : a > b) keys[i] = b, keys[p] = a;
+			}
+			__syncthreads();
+		}
 }
 
 // Leaf masks of the new rows: which leaves list the shooter's original triangle.  One warp per row, all rows
@@ -171,7 +209,6 @@ __device__ __forceinline__ void dbg_stamp(const FastState &F, int i) {
 
 __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
 	__shared__ bool s_last;
-	__shared__ int s_ntodo;
 	if (blockIdx.x == 0) dbg_stamp(F, 0);
 	const int T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	// thread t only sees receivers r == t (mod T); T is a multiple of kPredictGroups, so its running
@@ -190,41 +227,17 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	if (!s_last) return;
 	__threadfence();
 	dbg_stamp(F, 1);
-	// ---- last CTA: the `rows` largest group maxima.  Threads 0..255 own eight keys each; per round a thread
-	// maximum, an 8-warp reduction and one named barrier of 256 threads - the other 24 warps wait below.
-	__shared__ unsigned long long wmax[2][8];
-	__shared__ unsigned long long top[kMaxRows];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	// ---- last CTA: the `rows` largest group maxima = the head of a descending sort of the group keys
+	__shared__ unsigned long long keys[kPredictGroups];
+	__shared__ CacheScratch cs;
 	const int rows = F.rows;
-	if (threadIdx.x < kMaxRows) top[threadIdx.x] = 0ull;
-	__syncthreads();
-	if (threadIdx.x < 256) {
-		unsigned long long k[kPredictGroups / 256];
-#pragma unroll
-		for (int q = 0; q < kPredictGroups / 256; q++) {
-			k[q] = __ldcg(&F.group_key[threadIdx.x + 256 * q]);
-			F.group_key[threadIdx.x + 256 * q] = 0ull;	// ready for the next round
-		}
-		for (int it = 0; it < rows; it++) {
-			unsigned long long mine = 0ull;
-#pragma unroll
-			for (int q = 0; q < kPredictGroups / 256; q++) mine = k[q] > mine ? k[q] : mine;
-			const unsigned long long wm = warp_max_u64(mine);
-			if (lane == 0) wmax[it & 1][warp] = wm;
-			asm volatile("bar.sync 1, 256;" ::: "memory");
-			unsigned long long m = 0ull;
-#pragma unroll
-			for (int w = 0; w < 8; w++) m = wmax[it & 1][w] > m ? wmax[it & 1][w] : m;
-			if (m == 0ull) break;		// fewer candidates than rows (uniform across the 256 threads)
-			if (mine == m) {
-#pragma unroll
-				for (int q = 0; q < kPredictGroups / 256; q++)
-					if (k[q] == m) k[q] = 0ull;
-			}
-			if (threadIdx.x == 0) top[it] = m;
-		}
+	for (int q = threadIdx.x; q < kPredictGroups; q += blockDim.x) {
+		keys[q] = __ldcg(&F.group_key[q]);
+		F.group_key[q] = 0ull;	// ready for the next round
 	}
 	__syncthreads();
+	sort_keys_desc(keys, kPredictGroups);
+	const unsigned long long *top = keys;
 	dbg_stamp(F, 2);
 	__shared__ unsigned long long s_round;
 	if (threadIdx.x == 0) s_round = ++(*F.pred_round);	// rounds are numbered from 1 within a run epoch
@@ -264,33 +277,27 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 			*((volatile unsigned long long *)&F.box[threadIdx.x]->pred_seq[par][F.rank]) = s_round;
 		return;
 	}
-	// ---- warp 0 rebuilds the cache around the candidates: lane j owns candidate j and row j
-	if (warp == 0) {
-		if (lane == 0) *F.ticket = 0u;
-		int row;
-		const int nt = rebuild_cache(F, top, lane, &row);
-		if (lane == 0) {
-			s_ntodo = nt;
-			// the exact argmax (top[0]) is the next shooter
-			ShotRec h;
-			h.pad[0] = h.pad[1] = 0;
-			if (top[0] == 0ull) {
-				h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
-				*S.sel.converged = 1;
-			} else {
-				h.slot = (int)(top[0] & 0xffffffffu);
-				h.row = row;
-				const int r = S.slot_to_recv[h.slot];
-				h.dB[0] = S.st[0][r].w, h.dB[1] = S.st[1][r].w, h.dB[2] = S.st[2][r].w;
-				h.valid = 1;
-			}
-			*F.handoff = h;
-			F.counters[0] += (unsigned long long)nt, F.counters[1]++;
+	// ---- rebuild the cache around the candidates: thread j owns candidate j and row j
+	if (threadIdx.x == 0) *F.ticket = 0u;
+	const int nt = rebuild_cache(F, top, cs);
+	if (threadIdx.x == 0) {
+		// the exact argmax (top[0]) is the next shooter
+		ShotRec h;
+		h.pad[0] = h.pad[1] = 0;
+		if (top[0] == 0ull) {
+			h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
+			*S.sel.converged = 1;
+		} else {
+			h.slot = (int)(top[0] & 0xffffffffu);
+			h.row = cs.row[0];
+			const int r = S.slot_to_recv[h.slot];
+			h.dB[0] = S.st[0][r].w, h.dB[1] = S.st[1][r].w, h.dB[2] = S.st[2][r].w;
+			h.valid = 1;
 		}
+		*F.handoff = h;
+		F.counters[0] += (unsigned long long)nt, F.counters[1]++;
 	}
-	__syncthreads();
 	dbg_stamp(F, 3);
-	const int nt = s_ntodo;
 	if (threadIdx.x < nt) {	// K2 for the new rows, one thread each
 		const int row = F.todo[threadIdx.x];
 		build_shooter(S, S.slot_to_recv[F.row_slot[row]], &F.rec[row]);
@@ -302,13 +309,13 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	dbg_stamp(F, 5);
 }
 
-// Multi-GPU second half of the prediction (one CTA of 256 threads): wait for every rank's candidates,
+// Multi-GPU second half of the prediction (one CTA of 1024 threads): wait for every rank's candidates,
 // take the global top `rows`, rebuild the cache (identically on every rank), adopt the shooter records.
-__global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastState F) {
-	__shared__ unsigned long long wmax[2][8];
-	__shared__ unsigned long long top[kMaxRows];
+__global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastState F) {
+	__shared__ unsigned long long keys[kMaxWorld * kMaxRows];
 	__shared__ int top_src[kMaxRows];
-	__shared__ int s_ntodo, s_ok;
+	__shared__ CacheScratch cs;
+	__shared__ int s_ok;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned long long round = *F.pred_round;
 	const int par = (int)(round & 1ull);
@@ -330,51 +337,47 @@ __global__ void __launch_bounds__(256) predict_merge_kernel(DevScene S, FastStat
 		return;
 	}
 	const int rows = F.rows;
-	// thread t owns candidate (src = t / 32, j = t % 32)
-	const int src = threadIdx.x >> 5, j = threadIdx.x & 31;
+	// thread t owns candidate (src = t / kMaxRows, j = t % kMaxRows); a slot lives on one rank, so non-zero keys are unique
+	const int src = threadIdx.x / kMaxRows, j = threadIdx.x % kMaxRows;
 	unsigned long long k0 = 0ull;
 	if (src < F.world && j < rows) k0 = *((volatile unsigned long long *)&mine->pred[par][src][j].key);
-	for (int it = 0; it < rows; it++) {
-		const unsigned long long wm = warp_max_u64(k0);
-		if (lane == 0) wmax[it & 1][warp] = wm;
-		__syncthreads();
-		const unsigned long long m = warp_max_u64(lane < 8 ? wmax[it & 1][lane] : 0ull);
-		if (m != 0ull && k0 == m) k0 = 0ull, top_src[it] = threadIdx.x;
-		if (threadIdx.x == 0) top[it] = m;
-	}
+	keys[threadIdx.x] = k0;
+	if (threadIdx.x < kMaxRows) top_src[threadIdx.x] = 0;
 	__syncthreads();
-	if (warp == 0) {
-		int row;
-		const int nt = rebuild_cache(F, top, lane, &row);
-		if (lane == 0) {
-			s_ntodo = nt;
-			ShotRec h;
-			h.pad[0] = h.pad[1] = 0;
-			if (top[0] == 0ull) {
-				h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
-				*S.sel.converged = 1;
-			} else {
-				const PredCand *pc = &mine->pred[par][top_src[0] >> 5][top_src[0] & 31];
-				h.slot = (int)(top[0] & 0xffffffffu);
-				h.row = row;
-				h.dB[0] = *((volatile float *)&pc->rec.dB[0]), h.dB[1] = *((volatile float *)&pc->rec.dB[1]),
-				h.dB[2] = *((volatile float *)&pc->rec.dB[2]);
-				h.valid = 1;
-			}
-			*F.handoff = h;
-			F.counters[0] += (unsigned long long)nt, F.counters[1]++;
+	sort_keys_desc(keys, kMaxWorld * kMaxRows);
+	const unsigned long long *top = keys;
+	if (k0 != 0ull) {	// where did my key end up?  (binary search in the descending order)
+		int lo = 0, hi = kMaxWorld * kMaxRows - 1;
+		while (lo < hi) {
+			const int mid = (lo + hi) >> 1;
+			if (top[mid] > k0) lo = mid + 1; else hi = mid;
 		}
+		if (lo < rows) top_src[lo] = threadIdx.x;
 	}
 	__syncthreads();
-	const int nt = s_ntodo;
+	const int nt = rebuild_cache(F, top, cs);
+	if (threadIdx.x == 0) {
+		ShotRec h;
+		h.pad[0] = h.pad[1] = 0;
+		if (top[0] == 0ull) {
+			h.slot = -1, h.row = -1, h.dB[0] = h.dB[1] = h.dB[2] = 0.0f, h.valid = 0;
+			*S.sel.converged = 1;
+		} else {
+			const PredCand *pc = &mine->pred[par][top_src[0] / kMaxRows][top_src[0] % kMaxRows];
+			h.slot = (int)(top[0] & 0xffffffffu);
+			h.row = cs.row[0];
+			h.dB[0] = *((volatile float *)&pc->rec.dB[0]), h.dB[1] = *((volatile float *)&pc->rec.dB[1]),
+			h.dB[2] = *((volatile float *)&pc->rec.dB[2]);
+			h.valid = 1;
+		}
+		*F.handoff = h;
+		F.counters[0] += (unsigned long long)nt, F.counters[1]++;
+	}
 	// adopt the shooter records of the new rows from the mailbox (one warp per row, 4-byte granules)
-	for (int t = warp; t < nt; t += 8) {
+	for (int t = warp; t < nt; t += (int)(blockDim.x >> 5)) {
 		const int row = F.todo[t];
-		const int slot = F.row_slot[row];
-		int which = -1;
-		for (int i = 0; i < rows; i++)
-			if ((int)(top[i] & 0xffffffffu) == slot && top[i] != 0ull) which = top_src[i];
-		const volatile int *from = (const volatile int *)&mine->pred[par][which >> 5][which & 31].rec;
+		const int which = top_src[cs.todo_cand[t]];
+		const volatile int *from = (const volatile int *)&mine->pred[par][which / kMaxRows][which % kMaxRows].rec;
 		int *to = (int *)&F.rec[row];
 		for (int w = lane; w < (int)(sizeof(ShooterRec) / 4); w += 32) to[w] = from[w];
 	}
@@ -529,10 +532,15 @@ struct FFRows {	// form factor (both halves) of unique vertex u in cache row `ro
 	}
 };
 
-// One CTA of 256 threads.  Candidate i = cache row i (the slot F.row_slot[i]); warp 0 runs the chain with lane i
-// holding candidate i (the sequential restatement is chain_schedule_host in shot_core.cuh).
+// One CTA of 256 threads.  Candidate i = cache row i (the slot F.row_slot[i]); warp 0 runs the chain with lane l
+// holding candidates l, l + 32, ... (the sequential restatement is chain_schedule_host in shot_core.cuh).
+// Dynamic shared memory: rows x CandRec (the candidates' records with their rows x 3 table of form factors).
+constexpr int kChainPerLane = kMaxRows / 32;
+inline size_t chain_smem_bytes(int rows) { return (size_t)rows * sizeof(CandRec); }
+
 __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
-	__shared__ CandRec cm[kMaxRows];
+	extern __shared__ __align__(16) unsigned char chain_smem[];
+	CandRec *cm = (CandRec *)chain_smem;
 	__shared__ int s_owned[kMaxRows];
 	__shared__ int s_ok;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -544,12 +552,11 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 	// dependent round trips in all: directory -> receiver -> (state, vertex ids) -> form factors of every (candidate, row).
 	__shared__ int4 s_id[kMaxRows];
 	__shared__ int s_filled[kMaxRows];
-	if (threadIdx.x < kMaxRows) {
-		const int i = threadIdx.x;
+	for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) {
 		const int slot = i < rows ? F.row_slot[i] : -1;
 		const int r = slot >= 0 ? S.slot_to_recv[slot] : -1;
 		s_owned[i] = r >= 0, s_filled[i] = slot >= 0;
-		cm[i].slot = r >= 0 ? slot : -1;	// free row, or a candidate owned by another rank (filled in below)
+		if (i < rows) cm[i].slot = r >= 0 ? slot : -1;	// free row, or a candidate owned by another rank (filled in below)
 		if (r >= 0) {
 			const int4 id = __ldg(&S.vid[r]);
 			s_id[i] = id;
@@ -559,8 +566,8 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 		}
 	}
 	__syncthreads();
-	for (int q = threadIdx.x; q < kMaxRows * kMaxRows; q += 256) {	// (candidate i, row j)
-		const int i = q >> 5, j = q & 31;
+	for (int q = threadIdx.x; q < rows * rows; q += blockDim.x) {	// (candidate i, row j)
+		const int i = q / rows, j = q - i * rows;
 		if (!s_owned[i]) continue;
 		const bool filled = s_filled[j];
 		const int4 id = s_id[i];
@@ -569,6 +576,8 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 		cm[i].fsum[j][2] = filled ? ff_sum(F.ff, S.U, j, id.z) : 0.0f;
 	}
 	__syncthreads();
+	// what travels of a record: the header and the first `rows` entries of its form-factor table
+	const int rec_words = (int)(offsetof(CandRec, fsum) / 4) + 3 * rows;
 	if (F.world > 1) {
 		// publish the owned records to every other rank (4-byte granules, one warp per record), then the sequence number
 		for (int i = warp; i < rows; i += 8) {
@@ -577,7 +586,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 			for (int t = 0; t < F.world; t++) {
 				if (t == F.rank) continue;
 				volatile int *dst = (volatile int *)&F.box[t]->cand[par][i];
-				for (int w = lane; w < (int)(sizeof(CandRec) / 4); w += 32) dst[w] = src[w];
+				for (int w = lane; w < rec_words; w += 32) dst[w] = src[w];
 			}
 		}
 		__syncthreads();
@@ -593,7 +602,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 				if (s_owned[i] || F.row_slot[i] < 0) continue;
 				const volatile int *src = (const volatile int *)&mine->cand[par][i];
 				int *dst = (int *)&cm[i];
-				for (int w = lane; w < (int)(sizeof(CandRec) / 4); w += 32) dst[w] = src[w];
+				for (int w = lane; w < rec_words; w += 32) dst[w] = src[w];
 			}
 		}
 		__syncthreads();
@@ -603,27 +612,62 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 		if (lane == 0) *F.error = 1, *F.nsched = 0, *F.viol = 0;
 		return;
 	}
-	// ---- the chain: lane i replays the shots on candidate i
-	const bool valid = lane < rows && cm[lane].slot >= 0;
-	float4 a0 = cm[lane].a0, a1 = cm[lane].a1, a2 = cm[lane].a2;
-	const float fkx = cm[lane].fk[0], fky = cm[lane].fk[1], fkz = cm[lane].fk[2];
-	const int slot = valid ? cm[lane].slot : -1;
+	// ---- the chain: lane l replays the shots on candidates l + 32 c
+	float4 a0[kChainPerLane], a1[kChainPerLane], a2[kChainPerLane];
+	float fkx[kChainPerLane], fky[kChainPerLane], fkz[kChainPerLane];
+	int slot[kChainPerLane];
+	unsigned long long key[kChainPerLane];
+#pragma unroll
+	for (int c = 0; c < kChainPerLane; c++) {
+		const int i = lane + 32 * c;
+		const bool valid = i < rows && cm[i].slot >= 0;
+		slot[c] = valid ? cm[i].slot : -1;
+		if (valid) {
+			a0[c] = cm[i].a0, a1[c] = cm[i].a1, a2[c] = cm[i].a2;
+			fkx[c] = cm[i].fk[0], fky[c] = cm[i].fk[1], fkz[c] = cm[i].fk[2];
+		} else {
+			a0[c] = a1[c] = a2[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+			fkx[c] = fky[c] = fkz[c] = 0.f;
+		}
+		key[c] = valid ? energy_key(S.converge, a0[c].w, a1[c].w, a2[c].w, slot[c]) : 0ull;
+	}
 	const long long budget = *F.budget;
 	const int kmax = (int)(budget < (long long)kMaxChain ? (budget < 0 ? 0 : budget) : (long long)kMaxChain);
-	unsigned long long key = valid ? energy_key(S.converge, a0.w, a1.w, a2.w, slot) : 0ull;
-	unsigned long long best = warp_max_u64(key);
+	auto lane_best = [&]() {
+		unsigned long long m = 0ull;
+#pragma unroll
+		for (int c = 0; c < kChainPerLane; c++) m = key[c] > m ? key[c] : m;
+		return m;
+	};
+	unsigned long long best = warp_max_u64(lane_best());
 	int k = 0;
 	while (best != 0ull && k < kmax) {
-		const int b = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
-		const int sslot = __shfl_sync(0xffffffffu, slot, b);
-		const float sd0 = __shfl_sync(0xffffffffu, a0.w, b), sd1 = __shfl_sync(0xffffffffu, a1.w, b), sd2 = __shfl_sync(0xffffffffu, a2.w, b);
-		if (valid) {
-			if (slot == sslot) a0.w = a1.w = a2.w = 0.0f;	// rad.cpp:446-449
-			else if (unsaturated(a0, a1, a2))
-				apply_shot_ff(a0, a1, a2, fkx, fky, fkz, cm[lane].fsum[b][0], cm[lane].fsum[b][1], cm[lane].fsum[b][2], sd0, sd1, sd2);
-			key = energy_key(S.converge, a0.w, a1.w, a2.w, slot);
+		// the shooter: the lane that holds the best key (keys carry the slot, so non-zero keys are unique) and which of its candidates
+		int mine_c = -1;
+#pragma unroll
+		for (int c = 0; c < kChainPerLane; c++)
+			if (key[c] == best) mine_c = c;
+		const int bl = __ffs(__ballot_sync(0xffffffffu, mine_c >= 0)) - 1;
+		float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+		int ss = -1;
+#pragma unroll
+		for (int c = 0; c < kChainPerLane; c++)
+			if (c == mine_c) d0 = a0[c].w, d1 = a1[c].w, d2 = a2[c].w, ss = slot[c];
+		const int bc = __shfl_sync(0xffffffffu, mine_c, bl);
+		const int b = bl + 32 * bc;	// the shooter's candidate index = its cache row
+		const int sslot = __shfl_sync(0xffffffffu, ss, bl);
+		const float sd0 = __shfl_sync(0xffffffffu, d0, bl), sd1 = __shfl_sync(0xffffffffu, d1, bl), sd2 = __shfl_sync(0xffffffffu, d2, bl);
+#pragma unroll
+		for (int c = 0; c < kChainPerLane; c++) {
+			if (slot[c] < 0) continue;
+			if (slot[c] == sslot) a0[c].w = a1[c].w = a2[c].w = 0.0f;	// rad.cpp:446-449
+			else if (unsaturated(a0[c], a1[c], a2[c])) {
+				const float *f = cm[lane + 32 * c].fsum[b];
+				apply_shot_ff(a0[c], a1[c], a2[c], fkx[c], fky[c], fkz[c], f[0], f[1], f[2], sd0, sd1, sd2);
+			}
+			key[c] = energy_key(S.converge, a0[c].w, a1[c].w, a2[c].w, slot[c]);
 		}
-		best = warp_max_u64(key);
+		best = warp_max_u64(lane_best());
 		if (lane == 0) {
 			ShotSched s;
 			s.slot = sslot, s.row = b, s.dB[0] = sd0, s.dB[1] = sd1, s.dB[2] = sd2, s.pad = 0, s.next_key = best;

@@ -259,21 +259,43 @@ RADK_HD int any_hit_bounded_one(const DevTree &T, int entry, float px, float py,
 	return t != t ? 2 : 1;
 }
 
-// 0: nothing accepted under the bound, 1: some entry accepted (blocker), 2: an accepted entry has a NaN t
+// Can this entry give t = 0 / 0 ?  (a1 == 0 and a2 == 0: the ray starts in the occluder's plane and runs inside it.)
+// Such a t passes every test of TriHitted, also the inside test (all comparisons with NaN are false).
+RADK_HD bool entry_gives_nan(const DevTree &T, int entry, float px, float py, float pz, float vx, float vy, float vz, int ban) {
+	const int idx = entry & kIdMask;
+	if (idx == ban) return false;
+	const float4 *o = occ_plane(T, idx);
+	const float4 q0 = ldg(o), q1 = ldg(o + 1);
+	const float a2 = dot3(q0.w - px, q1.x - py, q1.y - pz, q0.x, q0.y, q0.z);
+	if (a2 != 0.0f && a2 == a2) return false;	// almost always: the origin is not in the plane
+	const float a1 = dot3(vx, vy, vz, q0.x, q0.y, q0.z);
+	const float t = a2 / a1;
+	return t != t;
+}
+
+// 0: nothing accepted under the bound, 1: some entry accepted (blocker) and no entry of the list gives a NaN t,
+// 2: an entry gives a NaN t (before or after the first blocker): the reference's answer then depends on the scan order
+// (a NaN t_min accepts every later entry, raycast.cpp:300,323-328), and the caller runs the sequential scan instead.
 RADK_HD int leaf_any_hit_bounded(const DevTree &T, int list4_off, float px, float py, float pz, float vx, float vy, float vz,
 				 int ban, float t_max, int tie) {
 	const int4 *l4 = T.list4 + list4_off;
+	bool blocked = false;
 	for (;;) {
 		const int4 id = ldg(l4++);
-		int r;
-		if (id.x < 0) return 0;
-		if ((r = any_hit_bounded_one(T, id.x, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
-		if (id.y < 0) return 0;
-		if ((r = any_hit_bounded_one(T, id.y, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
-		if (id.z < 0) return 0;
-		if ((r = any_hit_bounded_one(T, id.z, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
-		if (id.w < 0) return 0;
-		if ((r = any_hit_bounded_one(T, id.w, px, py, pz, vx, vy, vz, ban, t_max, tie))) return r;
+		const int e[4] = {id.x, id.y, id.z, id.w};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int k = 0; k < 4; k++) {
+			if (e[k] < 0) return blocked ? 1 : 0;
+			if (!blocked) {
+				const int r = any_hit_bounded_one(T, e[k], px, py, pz, vx, vy, vz, ban, t_max, tie);
+				if (r == 2) return 2;
+				blocked = r == 1;
+			} else if (entry_gives_nan(T, e[k], px, py, pz, vx, vy, vz, ban)) {
+				return 2;
+			}
+		}
 	}
 }
 
@@ -298,7 +320,9 @@ int leaf_visit_exact(const int *lp, const float4 *occ, int nocc, float px, float
 // One leaf visit of a shooter-visibility ray: -1 nothing hit here (walk on), 0 the walk ends on another
 // triangle, 1 the walk ends on logsrc.  Same answer as TriListHitted(...) compared with logsrc.
 RADK_HD int leaf_visit(const DevTree &T, int cur, bool lists_src, float px, float py, float pz, float vx, float vy, float vz,
-		       int ban, int logsrc) {
+		       int ban, int logsrc, bool exact = false) {
+	// exact: take the reference's sequential scan unconditionally (tests: the two scans must agree on every ray)
+	if (exact) return leaf_visit_exact(T.list + float_as_int_hd(leaf_lo(T, cur).w), T.occ, T.nocc, px, py, pz, vx, vy, vz, ban, logsrc);
 	float t_max = 1000000.0f;
 	int tie = -1;
 	bool src_hit = false;
@@ -308,7 +332,7 @@ RADK_HD int leaf_visit(const DevTree &T, int cur, bool lists_src, float px, floa
 	}
 	int r = (t_max != t_max) ? 2 : leaf_any_hit_bounded(T, ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban, t_max, tie);
 	if (r == 2) {
-		if (!lists_src) return 0;	// without logsrc in the list any acceptance ends the walk elsewhere
+		if (!lists_src) return 0;	// without logsrc in the list any acceptance (a NaN t is one) ends the walk elsewhere
 		return leaf_visit_exact(T.list + float_as_int_hd(leaf_lo(T, cur).w), T.occ, T.nocc, px, py, pz, vx, vy, vz, ban, logsrc);
 	}
 	if (r == 1) return 0;
@@ -318,7 +342,7 @@ RADK_HD int leaf_visit(const DevTree &T, int cur, bool lists_src, float px, floa
 // Is the shooter visible?  Same answer as (ray_walk(...) == logsrc); the walk of ff_batch_kernel.
 template <typename MaskPtr>
 RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, float pz, float vx, float vy, float vz,
-			      int ban, int logsrc) {
+			      int ban, int logsrc, bool exact = false) {
 	float t = 0.f;
 	int prev = -1, cur;
 	float qx = px, qy = py, qz = pz;
@@ -331,7 +355,7 @@ RADK_HD bool ray_sees(const DevTree &T, MaskPtr has_src, float px, float py, flo
 			if (++guard > 100000) return false;
 			continue;
 		}
-		const int v = leaf_visit(T, cur, (has_src[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc);
+		const int v = leaf_visit(T, cur, (has_src[cur >> 5] >> (cur & 31)) & 1u, px, py, pz, vx, vy, vz, ban, logsrc, exact);
 		if (v >= 0) return v == 1;
 		const float4 lo = leaf_lo(T, cur);
 		const float4 hi = leaf_hi(T, cur);

@@ -24,8 +24,16 @@
 
 namespace radk {
 
-constexpr int kMaxRows = 32;	// form-factor cache rows = candidates per round (one warp lane each)
-constexpr int kMaxChain = 64;	// shots scheduled per round at most
+#ifndef RADK_MAX_ROWS
+#define RADK_MAX_ROWS 128
+#endif
+#ifndef RADK_MAX_CHAIN
+#define RADK_MAX_CHAIN 192
+#endif
+constexpr int kMaxRows = RADK_MAX_ROWS;	// form-factor cache rows = candidates per round (a multiple of 32: kMaxRows / 32 per lane of the chain warp)
+constexpr int kMaxChain = RADK_MAX_CHAIN;	// shots scheduled per round at most (< 256: the violation mail carries it in 8 bits)
+static_assert(kMaxRows % 32 == 0 && kMaxRows <= 128, "one chain warp holds kMaxRows / 32 <= 4 candidates per lane");
+static_assert(kMaxChain < 255, "first violation travels in 8 bits");
 
 // key = (order-preserving bits of delta) << 32 | slot : lexicographic max == the reference's
 // sort-ascending-take-from-the-back over pair<float,int> (rad.cpp:398-402).

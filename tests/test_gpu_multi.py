@@ -50,6 +50,30 @@ def test_sharded_ranks_equal_single_gpu(hr, models_dir, name, world):
     assert owned_total == int((par1 >= 0).sum())
 
 
+def test_sharded_ranks_with_wide_candidate_sets(hr, models_dir):
+    """Three in-process ranks, 128 candidates per round: merge of 3 x 128 mailed candidates, records of 128 rows."""
+    m = hr.Model(str(models_dir / "model3s.tri"))
+    one = hr.Context(m, per_shot_kernels=1)
+    done1, conv1 = one.step(-1)
+    acc1, dB1, _ = one.download()
+    ctxs = [hr.Context(m, opts=hr.default_opts(rank=r, world=3, ff_rows=128)) for r in range(3)]
+    hr.Context.connect_local(ctxs)
+    res = [None] * 3
+
+    def work(r):
+        res[r] = ctxs[r].step(-1)
+    th = [threading.Thread(target=work, args=(r,)) for r in range(3)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert not any(t.is_alive() for t in th), "a rank hung"
+    for r, c in enumerate(ctxs):
+        assert res[r] == (done1, conv1) and c.shooter_log() == one.shooter_log()
+        own = c.owned_slots()
+        acc, dB, _ = c.download()
+        assert np.array_equal(acc[own].view(np.uint32), acc1[own].view(np.uint32))
+        assert np.array_equal(dB[own].view(np.uint32), dB1[own].view(np.uint32))
+
+
 def test_sharded_steps_in_pieces_and_rewind(hr, models_dir):
     m = hr.Model(str(models_dir / "model3s.tri"))
     one = hr.Context(m, per_shot_kernels=1)

@@ -164,6 +164,21 @@ def test_small_cache_and_budget_edges(hr, models_dir):
             assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
 
 
+@pytest.mark.parametrize("name,rows", [("church", 128), ("church", 64), ("model3s", 96), ("sbox", 128)])
+def test_wide_candidate_sets_match_golden(hr, golden, models_dir, name, rows):
+    """Up to 128 candidates per round (four per lane of the chain warp, bitonic top-K, CTA-wide cache rebuild): the
+    schedule gets longer and is cut by violations more often, the committed shots stay the reference's."""
+    g = golden["models"][name]["full"]
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    ctx = hr.Context(m, ff_rows=rows)
+    done, conv = ctx.step(-1)
+    assert conv and done == g["shots"]
+    assert ctx.shooter_log() == [s[0] for s in g["shooters"]]
+    ctx.download_into(m)
+    d = state_digest(m.triangles)
+    assert d["accB_sha"] == g["accB_sha"] and d["deltaB_sha"] == g["deltaB_sha"]
+
+
 def test_stats_off_gives_identical_state(hr, models_dir):
     m = hr.Model(str(models_dir / "sbox.tri"))
     a, b = hr.Context(m, collect_stats=1), hr.Context(m, collect_stats=0)
@@ -255,7 +270,7 @@ def test_ray_sees_matches_oracle(hr, po, models_dir):
         rng = np.random.default_rng(5)
         tri = m.triangles
         leaves = np.nonzero(tri["parent"] >= 0)[0]
-        mismatches = 0
+        mismatches = visible = 0
         for logsrc in rng.choice(np.unique(tri["parent"][leaves]), 6, replace=False):
             kids = leaves[tri["parent"][leaves] == logsrc]
             n = 30000
@@ -275,8 +290,9 @@ def test_ray_sees_matches_oracle(hr, po, models_dir):
             want = (sc.ray_hitted(p, v, frm) == logsrc).astype(np.int32)
             got = ctx.ray_sees(p, v, frm, int(logsrc))
             mismatches += int((got != want).sum())
-            assert want[k + 10:].sum() > 0                               # the sample does contain visible rays
+            visible += int(want[k + 10:].sum())
         assert mismatches == 0
+        assert visible > 0                                               # the sample does contain visible rays
 
 
 def test_select_matches_oracle(hr, po, models_dir):
