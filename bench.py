@@ -453,7 +453,7 @@ def run_ours(args):
         roof = {"bound": "fp32", "achieved": flops / step_s / 1e12, "peak": p_fp32 / 1e12, "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     dom = max(kt["ms"], key=lambda k: kt["ms"][k])
-    dom_name = {"form_factor": "ff_stream_kernel (K3a: culls + form factor + octree walk)", "update": "chain/apply/commit kernels (K3b)",
+    dom_name = {"form_factor": "ff_batch_kernel (K3a: culls + form factor + octree walk)", "update": "chain/apply/commit kernels (K3b)",
                 "select": "predict_kernel (K1+K2)"}[dom]
     traffic = kprof.get(dom, {}).get("dram_bytes_per_launch") if world == 1 else None
     roof.update({

@@ -76,12 +76,16 @@ RADK_HD void apply_shot_ff(float4 &a0, float4 &a1, float4 &a2, float fkx, float 
 	a0.w = dB[0], a1.w = dB[1], a2.w = dB[2];
 }
 
-// One scheduled shot: who shoots, from which cache row, with which unshot energy, and the key of the shooter
-// scheduled after it (0: none) - a receiver whose key exceeds next_key after this shot breaks the schedule.
+// One scheduled shot: who shoots, from which cache row, with which unshot energy.  With -parallel_src P > 1 an
+// iteration of the reference's loop (rad.cpp:406-451) has up to P co-shooters: its entries are consecutive, the first
+// carries kSchedHead, the last kSchedLast (P = 1: every entry carries both).  next_key (on the last entry of an
+// iteration) is the smallest key among the shooters scheduled for the NEXT iteration (0: none scheduled) - a receiver
+// whose own key exceeds it after this iteration would have been selected instead and breaks the schedule.
+constexpr int kSchedHead = 1, kSchedLast = 2;
 struct alignas(32) ShotSched {
 	int slot, row;
 	float dB[3];
-	int pad;
+	int flags;
 	unsigned long long next_key;
 };
 
@@ -94,40 +98,86 @@ struct alignas(16) CandRec {
 	float fsum[kMaxRows][3];
 };
 
-// Sequential restatement of the chain (the device runs it with one warp lane per candidate, fast_kernels.cuh):
-// replays shots on the candidate records only.  Returns the number of scheduled shots (<= max_shots, kMaxChain).
-inline int chain_schedule_host(CandRec *c, int rows, float converge, long long max_shots, ShotSched *out) {
+// listCanditate's shooter count (rad.cpp:400): n = min((|C| + 4) / 5, ParallelSource), |C| = receivers whose unshot
+// energy exceeds the limit.  The chain knows |C| exactly only at the start of a round (the selection pass counts it);
+// afterwards it knows a lower bound (each shooter leaves C, receivers may enter it).  n is certain while the bound
+// gives P already: lb >= 5 P - 4.
+RADK_HD int shooters_for(long long count, int P) {
+	const long long n = (count + 4) / 5;
+	return (int)(n < (long long)P ? n : (long long)P);
+}
+RADK_HD bool shooter_count_certain(long long count_lb, int P) { return P <= 1 || count_lb >= 5ll * P - 4; }
+
+// Sequential restatement of the chain (the device runs it with one warp, fast_kernels.cuh): replays the iterations on
+// the candidate records only.  `count` = |C| at the start of the round (only read when P > 1), max_iters = iterations
+// the caller may still run.  Returns the number of schedule entries (<= kMaxChain); *iters_out = iterations scheduled.
+inline int chain_schedule_host(CandRec *c, int rows, float converge, long long max_iters, int P, long long count, ShotSched *out,
+			       int *iters_out = nullptr) {
 	unsigned long long key[kMaxRows];
-	auto best_of = [&](int *who) {
-		unsigned long long best = 0ull;
-		for (int i = 0; i < rows; i++) {
-			key[i] = c[i].slot >= 0 ? energy_key(converge, c[i].a0.w, c[i].a1.w, c[i].a2.w, c[i].slot) : 0ull;
-			if (key[i] > best) best = key[i], *who = i;
-		}
-		return best;
+	int sel[kMaxRows];
+	auto keys = [&]() {
+		for (int i = 0; i < rows; i++) key[i] = c[i].slot >= 0 ? energy_key(converge, c[i].a0.w, c[i].a1.w, c[i].a2.w, c[i].slot) : 0ull;
 	};
-	int b = -1, k = 0;
-	unsigned long long best = best_of(&b);
-	while (best != 0ull && k < kMaxChain && (long long)k < max_shots) {
-		ShotSched s;
-		s.slot = c[b].slot, s.row = b, s.dB[0] = c[b].a0.w, s.dB[1] = c[b].a1.w, s.dB[2] = c[b].a2.w, s.pad = 0;
+	// the n largest keys, descending, into sel[]; false when the candidates cannot supply n shooters
+	auto select = [&](int n) {
+		bool used[kMaxRows] = {};
+		for (int j = 0; j < n; j++) {
+			int b = -1;
+			for (int i = 0; i < rows; i++)
+				if (!used[i] && key[i] != 0ull && (b < 0 || key[i] > key[b])) b = i;
+			if (b < 0) return false;
+			used[b] = true, sel[j] = b;
+		}
+		return true;
+	};
+	int k = 0, iters = 0, last = -1;
+	long long lb = count;
+	keys();
+	while ((long long)iters < max_iters) {
+		if (iters > 0 && !shooter_count_certain(lb, P)) break;
+		const int n = P <= 1 ? 1 : shooters_for(lb, P);
+		if (n <= 0 || k + n > kMaxChain || !select(n)) break;
+		if (last >= 0) out[last].next_key = key[sel[n - 1]];
+		for (int j = 0; j < n; j++) {
+			const CandRec &s = c[sel[j]];
+			ShotSched e;
+			e.slot = s.slot, e.row = sel[j], e.dB[0] = s.a0.w, e.dB[1] = s.a1.w, e.dB[2] = s.a2.w;
+			e.flags = (j == 0 ? kSchedHead : 0) | (j == n - 1 ? kSchedLast : 0);
+			e.next_key = 0ull;
+			out[k + j] = e;
+		}
 		for (int i = 0; i < rows; i++) {
 			if (c[i].slot < 0) continue;
-			if (c[i].slot == s.slot) c[i].a0.w = c[i].a1.w = c[i].a2.w = 0.0f;	// rad.cpp:446-449
-			else if (unsaturated(c[i].a0, c[i].a1, c[i].a2))
+			bool shoots = false;
+			for (int j = 0; j < n; j++) shoots |= sel[j] == i;
+			if (shoots) continue;		// rad.cpp:421-422: co-shooters do not receive
+			if (!unsaturated(c[i].a0, c[i].a1, c[i].a2)) continue;	// rad.cpp:424-428: checked once per iteration
+			for (int j = 0; j < n; j++) {
+				const int b = sel[j];
 				apply_shot_ff(c[i].a0, c[i].a1, c[i].a2, c[i].fk[0], c[i].fk[1], c[i].fk[2], c[i].fsum[b][0], c[i].fsum[b][1],
-					      c[i].fsum[b][2], s.dB[0], s.dB[1], s.dB[2]);
+					      c[i].fsum[b][2], out[k + j].dB[0], out[k + j].dB[1], out[k + j].dB[2]);
+			}
 		}
-		best = best_of(&b);
-		s.next_key = best;
-		out[k++] = s;
+		for (int j = 0; j < n; j++) c[sel[j]].a0.w = c[sel[j]].a1.w = c[sel[j]].a2.w = 0.0f;	// rad.cpp:446-449
+		last = k + n - 1;
+		k += n, iters++, lb -= n;
+		keys();
 	}
+	if (last >= 0 && out[last].next_key == 0ull) {
+		// key of the shooter that would come next if the round went on (P = 1: the violation test of the last shot is
+		// harmless either way - nothing scheduled follows it)
+		unsigned long long best = 0ull;
+		for (int i = 0; i < rows; i++) best = key[i] > best ? key[i] : best;
+		out[last].next_key = P <= 1 ? best : ~0ull;
+	}
+	if (iters_out) *iters_out = iters;
 	return k;
 }
 
-// The apply pass of one receiver: shots [0, n) of the schedule on (a0, a1, a2).  ff(row, vertex id) returns the cached
-// form factor pair of a unique vertex.  Returns the first shot after which this receiver's key exceeds the scheduled
-// next shooter's key (n: none).
+// The apply pass of one receiver: entries [0, n) of the schedule (n ends an iteration) on (a0, a1, a2).  ff(row, vertex
+// id) returns the cached form factor pair of a unique vertex.  Returns the index of the LAST entry of the first
+// iteration after which the schedule no longer holds for this receiver (n: none): its key exceeds next_key, or it left
+// the candidate set without shooting (a NaN energy; the chain's lower bound on |C| would be wrong).
 template <typename FF>
 RADK_HD int apply_schedule(float4 &a0, float4 &a1, float4 &a2, int id0, int id1, int id2, float fkx, float fky, float fkz,
 			   int slot, const ShotSched *sched, int n, float converge, FF ff) {
@@ -135,6 +185,7 @@ RADK_HD int apply_schedule(float4 &a0, float4 &a1, float4 &a2, int id0, int id1,
 	// the form factors of a shot do not depend on the receiver's state: those of kChunk shots are fetched together
 	// (independent loads in flight) before the shots are applied in order
 	constexpr int kChunk = 8;
+	bool shoots = false, receive = false, was_cand = false;
 	for (int k0 = 0; k0 < n; k0 += kChunk) {
 		float f[kChunk][3];
 #if defined(__CUDA_ARCH__)
@@ -151,12 +202,19 @@ RADK_HD int apply_schedule(float4 &a0, float4 &a1, float4 &a2, int id0, int id1,
 			const int k = k0 + j;
 			if (k >= n) break;
 			const ShotSched &s = sched[k];
-			if (slot == s.slot) {
-				a0.w = a1.w = a2.w = 0.0f;
-			} else if (unsaturated(a0, a1, a2)) {
-				apply_shot_ff(a0, a1, a2, fkx, fky, fkz, f[j][0], f[j][1], f[j][2], s.dB[0], s.dB[1], s.dB[2]);
+			if (s.flags & kSchedHead) {
+				// is this receiver one of the iteration's shooters (rad.cpp:421-422) ?  eligible otherwise (424-428) ?
+				shoots = slot == s.slot;
+				for (int q = k; !(sched[q].flags & kSchedLast); q++) shoots |= slot == sched[q + 1].slot;
+				receive = !shoots && unsaturated(a0, a1, a2);
+				was_cand = energy_key(converge, a0.w, a1.w, a2.w, slot) != 0ull;
 			}
-			if (viol == n && energy_key(converge, a0.w, a1.w, a2.w, slot) > s.next_key) viol = k;
+			if (receive) apply_shot_ff(a0, a1, a2, fkx, fky, fkz, f[j][0], f[j][1], f[j][2], s.dB[0], s.dB[1], s.dB[2]);
+			if (s.flags & kSchedLast) {
+				if (shoots) a0.w = a1.w = a2.w = 0.0f;
+				const unsigned long long key = energy_key(converge, a0.w, a1.w, a2.w, slot);
+				if (viol == n && (key > s.next_key || (was_cand && !shoots && key == 0ull))) viol = k;
+			}
 		}
 	}
 	return viol;

@@ -284,6 +284,8 @@ struct EmuShard {
 	std::vector<float4> prev[3];
 	ShotSched sched[kMaxChain];
 	int nsched = 0;
+	int parallel_src = 1;			// -parallel_src: co-shooters per iteration
+	long long local_count = 0;		// receivers of this shard above the convergence limit (emu_shard_top)
 	long long rows_filled = 0, rounds = 0, reapplied = 0;
 };
 
@@ -301,6 +303,8 @@ extern "C" void *emu_shard_open(const radk_scene *s, int rank, int world, int ro
 }
 extern "C" void emu_shard_close(void *h) { delete (EmuShard *)h; }
 extern "C" int emu_shard_sizes(void *h, int *R, int *U) { EmuShard *e = (EmuShard *)h; *R = e->F.R, *U = e->F.U; return 0; }
+extern "C" void emu_shard_set_parallel_src(void *h, int P) { ((EmuShard *)h)->parallel_src = P < 1 ? 1 : P; }
+extern "C" long long emu_shard_count(void *h) { return ((EmuShard *)h)->local_count; }
 extern "C" int emu_shooter_rec_bytes(void) { return (int)sizeof(ShooterRec); }
 extern "C" int emu_cand_rec_bytes(void) { return (int)sizeof(CandRec); }
 
@@ -321,6 +325,7 @@ extern "C" int emu_shard_top(void *h, unsigned long long *keys, ShooterRec *recs
 		const unsigned long long k = energy_key(e->converge, F.st[0][r].w, F.st[1][r].w, F.st[2][r].w, F.recv_slot[r]);
 		if (k) all.push_back(k);
 	}
+	e->local_count = (long long)all.size();
 	const size_t n = std::min<size_t>(all.size(), (size_t)e->rows);
 	std::partial_sort(all.begin(), all.begin() + n, all.end(), std::greater<unsigned long long>());
 	for (int i = 0; i < e->rows; i++) {
@@ -414,12 +419,14 @@ extern "C" int emu_shard_cands(void *h, CandRec *out, int *owned) {
 	return 0;
 }
 
-extern "C" int emu_shard_chain(void *h, const CandRec *cands, long long budget) {
+// count = receivers above the convergence limit over all ranks (sum of emu_shard_count), budget in iterations
+extern "C" int emu_shard_chain2(void *h, const CandRec *cands, long long budget, long long count) {
 	EmuShard *e = (EmuShard *)h;
 	std::vector<CandRec> c(cands, cands + e->rows);
-	e->nsched = chain_schedule_host(c.data(), e->rows, e->converge, budget, e->sched);
+	e->nsched = chain_schedule_host(c.data(), e->rows, e->converge, budget, e->parallel_src, count, e->sched);
 	return e->nsched;
 }
+extern "C" int emu_shard_chain(void *h, const CandRec *cands, long long budget) { return emu_shard_chain2(h, cands, budget, 0); }
 
 extern "C" int emu_shard_apply(void *h) {
 	EmuShard *e = (EmuShard *)h;
@@ -437,7 +444,8 @@ extern "C" int emu_shard_apply(void *h) {
 	return viol;
 }
 
-// viol = minimum over the ranks; returns the number of committed shots and their shooter slots
+// viol = minimum over the ranks; returns the number of committed iterations and the first shooter of each (what the
+// reference's loop counter / the shot log see)
 extern "C" int emu_shard_commit(void *h, int viol, int *slots) {
 	EmuShard *e = (EmuShard *)h;
 	FlatScene &F = e->F;
@@ -452,8 +460,10 @@ extern "C" int emu_shard_commit(void *h, int viol, int *slots) {
 		}
 		e->reapplied++;
 	}
-	for (int k = 0; k < n; k++) slots[k] = e->sched[k].slot;
-	return n;
+	int iters = 0;
+	for (int k = 0; k < n; k++)
+		if (e->sched[k].flags & kSchedHead) slots[iters++] = e->sched[k].slot;
+	return iters;
 }
 
 // owned slots and their state: slots[R], accB[R][9], deltaB[R][3]
@@ -472,11 +482,15 @@ extern "C" int emu_shard_state(void *h, int *slots, float *accB, float *deltaB) 
 
 // The whole chained loop for `world` ranks in one process: accB[trinum][3][3], deltaB[trinum][3] by slot, shooter slots.
 // counters: [0] rows filled (rank 0), [1] rounds, [2] rounds that re-applied a prefix.
+static int g_parallel_src = 1;
+extern "C" void emu_set_parallel_src(int P) { g_parallel_src = P < 1 ? 1 : P; }
 extern "C" int emu_run_chain(const radk_scene *s, float converge, int world, int rows, int shots, float *accB, float *deltaB,
 			      int *shooters, int *nshots_out, long long *counters) {
 	std::vector<EmuShard *> sh(world);
-	for (int w = 0; w < world; w++)
+	for (int w = 0; w < world; w++) {
 		if (!(sh[w] = (EmuShard *)emu_shard_open(s, w, world, rows, converge))) return 1;
+		emu_shard_set_parallel_src(sh[w], g_parallel_src);
+	}
 	int done = 0;
 	std::vector<unsigned long long> keys((size_t)world * rows), top(rows);
 	std::vector<ShooterRec> recs((size_t)world * rows), toprec(rows);
@@ -497,7 +511,9 @@ extern "C" int emu_run_chain(const radk_scene *s, float converge, int world, int
 				if (owned[i]) cands[i] = mine[i];
 		}
 		int K = 0, viol = kMaxChain + 1;
-		for (int w = 0; w < world; w++) K = emu_shard_chain(sh[w], cands.data(), shots - done);
+		long long count = 0;
+		for (int w = 0; w < world; w++) count += sh[w]->local_count;
+		for (int w = 0; w < world; w++) K = emu_shard_chain2(sh[w], cands.data(), shots - done, count);
 		for (int w = 0; w < world; w++) viol = std::min(viol, emu_shard_apply(sh[w]));
 		int n = 0;
 		for (int w = 0; w < world; w++) n = emu_shard_commit(sh[w], viol, slots.data());

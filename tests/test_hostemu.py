@@ -158,3 +158,28 @@ def test_chained_shot_loop_matches_oracle(hr, po, emu, models_dir, name, shots, 
     assert np.array_equal(accB[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
     assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
     assert cnt[1] <= max(1, ns.value)              # rounds
+
+
+@pytest.mark.parametrize("name,P,shots,world,rows", [("sbox", 4, -1, 1, 32), ("sbox", 4, -1, 2, 8), ("sbox", 10, 40, 3, 64),
+                                                     ("blocks", 6, -1, 2, 32), ("model3s", 3, -1, 1, 32)])
+def test_chained_loop_with_parallel_sources_matches_oracle(hr, po, emu, models_dir, name, P, shots, world, rows):
+    """-parallel_src P on the chained loop: an iteration = min((|C|+4)/5, P) co-shooters (rad.cpp:387-451); the shooter
+    count is only scheduled ahead while the lower bound on |C| makes it certain.  Same iterations, same bits."""
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    sc = oracle_scene(po, m, parallel_src=P)
+    seq = sc.run(None if shots < 0 else shots)
+    n = m.trinum
+    accB, dB = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3), np.float32)
+    sh = np.zeros(max(len(seq), 1), np.int32)
+    ns = C.c_int()
+    cnt = (C.c_longlong * 8)()
+    emu.emu_set_parallel_src(P)
+    try:
+        assert emu.emu_run_chain(C.addressof(m.scene), 1200.0, world, rows, len(seq) if shots < 0 else shots, accB.ctypes.data,
+                                 dB.ctypes.data, sh.ctypes.data, C.byref(ns), cnt) == 0
+    finally:
+        emu.emu_set_parallel_src(1)
+    live = sc.slots["parent"] >= 0
+    assert list(sh[: ns.value]) == [s[0] for s in seq]
+    assert np.array_equal(accB[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
+    assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
