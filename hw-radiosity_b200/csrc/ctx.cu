@@ -101,6 +101,8 @@ struct radk_ctx {
 	DevBuf<PeerBox> box;
 	DevBuf<unsigned long long> pred_round;
 	DevBuf<int> fast_error;
+	DevBuf<unsigned long long> exact;	// -parallel_src: threshold, list length, collected keys, sorted group maxima
+	DevBuf<long long> cand_count;
 	DevBuf<unsigned long long> dbg;
 	std::vector<void *> ipc_opened;
 	bool peers_connected = false;
@@ -211,6 +213,8 @@ int reset_fast_state(radk_ctx *c) {
 	CUDA_TRY(cudaMemsetAsync(c->budget.p, 0, sizeof(long long), st));
 	CUDA_TRY(cudaMemsetAsync(c->fast_error.p, 0, sizeof(int), st));
 	CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->exact.p, 0, (2 + kExactCap + kMaxRows) * sizeof(unsigned long long), st));
+	CUDA_TRY(cudaMemsetAsync(c->cand_count.p, 0, sizeof(long long), st));
 	c->epoch_word = (++c->epoch) << 40;	// stale mailbox sequence numbers of earlier runs can never match
 	CUDA_TRY(cudaMemcpyAsync(c->pred_round.p, &c->epoch_word, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
 	return RADK_OK;
@@ -224,6 +228,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	F.cond = 0;	// host-launched rounds: no graph condition to set
 	if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
 	predict_kernel<<<64, 1024, 0, st>>>(c->S, F);
+	if (c->F.parallel_src > 1) { predict_exact_kernel<<<64, 1024, 0, st>>>(c->S, F); c->launches++; }
 	if (c->F.world > 1) { predict_merge_kernel<<<1, 1024, 0, st>>>(c->S, F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
@@ -261,6 +266,7 @@ bool build_loop_graph(radk_ctx *c) {
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
 	std::vector<K> ks;
 	ks.push_back({(const void *)predict_kernel, dim3(64), dim3(1024), 0});
+	if (c->F.parallel_src > 1) ks.push_back({(const void *)predict_exact_kernel, dim3(64), dim3(1024), 0});
 	if (c->F.world > 1) ks.push_back({(const void *)predict_merge_kernel, dim3(1), dim3(1024), 0});
 	ks.push_back({(const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock), 0});
 	ks.push_back({(const void *)chain_kernel, dim3(1), dim3(256), chain_smem_bytes(c->rows)});
@@ -504,9 +510,12 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		// by the work speculation wastes when long schedules are cut short (measured, profiles/README.md round 2).  The
 		// rule only uses numbers every rank agrees on.
 		const char *env_rows = getenv("RADK_FF_ROWS");
-		const int def_rows = F.leaves_total / world < 50000 ? 64 : 32;
+		// -parallel_src P: an iteration needs P rows at once; four iterations per round where kMaxRows allows it
+		const int P = std::max(1, std::min(o.parallel_src, kMaxSources));
+		const int def_rows = P > 1 ? std::min(kMaxRows, std::max(32, (4 * P + 31) / 32 * 32)) : (F.leaves_total / world < 50000 ? 64 : 32);
 		int rows = o.ff_rows > 0 ? std::min(o.ff_rows, kMaxRows) : (env_rows && atoi(env_rows) > 0 ? std::min(atoi(env_rows), kMaxRows) : def_rows);
 		while (rows > 2 && (size_t)rows * std::max(U, 1) * sizeof(float2) > free_b / 4) rows >>= 1;
+		if (rows < P) { set_error("the form-factor cache cannot hold one row per -parallel_src shooter"); return RADK_ERR_LIMIT; }
 		c->rows = rows;
 		CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes(kMaxRows)));
 		CUDA_TRY(c->ffcache.alloc((size_t)rows * std::max(U, 1)));
@@ -525,6 +534,8 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		CUDA_TRY(c->box.alloc(1));
 		CUDA_TRY(c->pred_round.alloc(1));
 		CUDA_TRY(c->fast_error.alloc(1));
+		CUDA_TRY(c->exact.alloc(2 + kExactCap + kMaxRows));
+		CUDA_TRY(c->cand_count.alloc(1));
 		CUDA_TRY(cudaMemsetAsync(c->box.p, 0, sizeof(PeerBox), st));
 		const int mask_words = (s->nnodes + 31) / 32;
 		CUDA_TRY(c->row_mask.alloc((size_t)kMaxRows * mask_words));
@@ -541,6 +552,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.box[o.rank] = c->box.p;
 		F.rank = o.rank, F.world = world;
 		F.pred_round = c->pred_round.p, F.error = c->fast_error.p;
+		F.parallel_src = P, F.local_count = c->fast_uints.p + 2, F.cand_count = c->cand_count.p, F.exact = c->exact.p;
 		F.dbg = nullptr;
 		if (getenv("RADK_DEBUG_PREDICT")) { CUDA_TRY(c->dbg.alloc(16)); CUDA_TRY(cudaMemsetAsync(c->dbg.p, 0, 16 * 8, st)); F.dbg = c->dbg.p; }
 		c->peers_connected = world == 1;
@@ -628,6 +640,7 @@ int read_flags(radk_ctx *c) {
 		CUDA_TRY(cudaMemcpyAsync(c->h_error, c->fast_error.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	}
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if (c->use_fast && *c->h_error == 2) { set_error("-parallel_src selection: more than 2048 receivers above the selection threshold share fewer than P selection groups"); return RADK_ERR_LIMIT; }
 	if (c->use_fast && *c->h_error) { set_error("a peer rank did not answer within the device-side timeout"); return RADK_ERR_STATE; }
 	return RADK_OK;
 }
@@ -653,7 +666,9 @@ int radk_ctx_create(const radk_scene *s, const radk_opts *o, radk_ctx **out) {
 	radk_ctx *c = new radk_ctx();
 	c->opt = opt;
 	c->device = opt.device;
-	c->use_dedup = opt.dedup >= 0 && opt.parallel_src <= 1;
+	// vertex sharing + form-factor cache: single-source always, -parallel_src > 1 on the batched path only (statistics
+	// mode and per-shot kernels take the generic per-receiver kernel)
+	c->use_dedup = opt.dedup >= 0 && (opt.parallel_src <= 1 || (!opt.collect_stats && !opt.per_shot_kernels));
 	int rc = RADK_OK;
 	do {
 		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||

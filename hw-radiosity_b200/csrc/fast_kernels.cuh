@@ -89,7 +89,14 @@ struct FastState {
 	unsigned *apply_ticket;		// last-CTA-done counter of apply_kernel (multi-GPU: the last CTA mails viol)
 	float4 *st_prev[3];		// [R] the receivers' state before the round's apply pass
 	unsigned long long *counters;	// [8] 0: rows filled, 1: rounds, 2: shots scheduled, 3: shots committed, 4: rounds that re-applied
+	// -parallel_src P > 1 (an iteration shoots min((|C| + 4) / 5, P) patches, rad.cpp:387-404)
+	int parallel_src;
+	unsigned *local_count;		// receivers of this shard above the convergence limit, counted by predict_kernel's scan
+	long long *cand_count;		// |C| over all ranks at the start of the round (read by chain_kernel)
+	unsigned long long *exact;	// [0] threshold T (the P-th largest group maximum), [1] list length, [2..2+kExactCap) every key >= T,
+					// [2+kExactCap .. +kMaxRows) the sorted group maxima: see predict_exact_kernel
 };
+constexpr int kExactCap = 2048;	// keys the exact selection pass can collect (= kPredictGroups: sorted in the same shared array)
 
 // Spin until *p == expected (p is in local memory, written by a peer).  Gives up after ~20 s of SM
 // clock so that a dead peer cannot hang the GPU; the caller then flags an error.
@@ -207,37 +214,10 @@ __device__ __forceinline__ void dbg_stamp(const FastState &F, int i) {
 	}
 }
 
-__global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
-	__shared__ bool s_last;
-	if (blockIdx.x == 0) dbg_stamp(F, 0);
-	const int T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-	// thread t only sees receivers r == t (mod T); T is a multiple of kPredictGroups, so its running
-	// maximum belongs to group t % kPredictGroups
-	unsigned long long best = 0ull;
-	for (int r = gtid; r < S.R; r += T) {
-		unsigned c;
-		const unsigned long long k = candidate_key(S, S.st[0][r].w, S.st[1][r].w, S.st[2][r].w, __ldg(&S.slot[r]), ~0ull, &c);
-		best = k > best ? k : best;
-	}
-	if (best) atomicMax(&F.group_key[gtid & (kPredictGroups - 1)], best);
-	__threadfence();
-	__syncthreads();
-	if (threadIdx.x == 0) s_last = (atomicAdd(F.ticket, 1u) == gridDim.x - 1);
-	__syncthreads();
-	if (!s_last) return;
-	__threadfence();
-	dbg_stamp(F, 1);
-	// ---- last CTA: the `rows` largest group maxima = the head of a descending sort of the group keys
-	__shared__ unsigned long long keys[kPredictGroups];
-	__shared__ CacheScratch cs;
+// Tail of the prediction, run by ONE CTA of 1024 threads with the candidate keys top[0 .. rows) sorted descending in
+// shared memory: multi-GPU - mail the local candidates; single GPU - rebuild the cache, shooter records, leaf masks.
+__device__ void predict_finish(const DevScene &S, const FastState &F, const unsigned long long *top, CacheScratch &cs) {
 	const int rows = F.rows;
-	for (int q = threadIdx.x; q < kPredictGroups; q += blockDim.x) {
-		keys[q] = __ldcg(&F.group_key[q]);
-		F.group_key[q] = 0ull;	// ready for the next round
-	}
-	__syncthreads();
-	sort_keys_desc(keys, kPredictGroups);
-	const unsigned long long *top = keys;
 	dbg_stamp(F, 2);
 	__shared__ unsigned long long s_round;
 	if (threadIdx.x == 0) s_round = ++(*F.pred_round);	// rounds are numbered from 1 within a run epoch
@@ -249,7 +229,8 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		const int par = (int)(s_round & 1ull);
 		if (threadIdx.x < rows) {
 			PredCand pc;
-			pc.key = top[threadIdx.x], pc.pad[0] = rows, pc.pad[1] = 0;	// pad[0]: every rank must run the same cache size
+			pc.key = top[threadIdx.x], pc.pad[0] = rows;	// pad[0]: every rank must run the same cache size
+			pc.pad[1] = (int)*F.local_count;	// pad[1] (read from entry 0): this rank's part of |C|
 			pc.rec.valid = 0;
 			// the record only travels when no rank has it yet (the caches are identical on all ranks)
 			const bool fresh = pc.key != 0ull && F.slot_row[(int)(pc.key & 0xffffffffu)] < 0;
@@ -261,6 +242,7 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 				} else {	// key + current unshot energy (the handoff needs it if this candidate is the global best)
 					*((volatile unsigned long long *)&dst->key) = pc.key;
 					*((volatile int *)&dst->pad[0]) = rows;
+					*((volatile int *)&dst->pad[1]) = pc.pad[1];
 					if (pc.key != 0ull) {
 						const int r = S.slot_to_recv[(int)(pc.key & 0xffffffffu)];
 						*((volatile float *)&dst->rec.dB[0]) = S.st[0][r].w;
@@ -275,6 +257,8 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		__syncthreads();
 		if (threadIdx.x < F.world)
 			*((volatile unsigned long long *)&F.box[threadIdx.x]->pred_seq[par][F.rank]) = s_round;
+		__syncthreads();	// every thread has read the count it mails
+		if (threadIdx.x == 0) *F.local_count = 0u;
 		return;
 	}
 	// ---- rebuild the cache around the candidates: thread j owns candidate j and row j
@@ -296,6 +280,8 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		}
 		*F.handoff = h;
 		F.counters[0] += (unsigned long long)nt, F.counters[1]++;
+		*F.cand_count = (long long)*F.local_count;
+		*F.local_count = 0u;
 	}
 	dbg_stamp(F, 3);
 	if (threadIdx.x < nt) {	// K2 for the new rows, one thread each
@@ -307,6 +293,112 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 	build_row_masks(S, F, nt);
 	__syncthreads();
 	dbg_stamp(F, 5);
+}
+
+__global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
+	__shared__ bool s_last;
+	if (blockIdx.x == 0) dbg_stamp(F, 0);
+	const int T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	// thread t only sees receivers r == t (mod T); T is a multiple of kPredictGroups, so its running
+	// maximum belongs to group t % kPredictGroups
+	unsigned long long best = 0ull;
+	unsigned ncand = 0u;
+	for (int r = gtid; r < S.R; r += T) {
+		unsigned c;
+		const unsigned long long k = candidate_key(S, S.st[0][r].w, S.st[1][r].w, S.st[2][r].w, __ldg(&S.slot[r]), ~0ull, &c);
+		best = k > best ? k : best;
+		ncand += c;
+	}
+	if (best) atomicMax(&F.group_key[gtid & (kPredictGroups - 1)], best);
+	if (F.parallel_src > 1) {	// |C| of listCanditate (rad.cpp:400)
+		ncand = __reduce_add_sync(0xffffffffu, ncand);
+		if ((threadIdx.x & 31) == 0 && ncand) atomicAdd(F.local_count, ncand);
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = (atomicAdd(F.ticket, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	dbg_stamp(F, 1);
+	// ---- last CTA: the `rows` largest group maxima = the head of a descending sort of the group keys
+	__shared__ unsigned long long keys[kPredictGroups];
+	__shared__ CacheScratch cs;
+	for (int q = threadIdx.x; q < kPredictGroups; q += blockDim.x) {
+		keys[q] = __ldcg(&F.group_key[q]);
+		F.group_key[q] = 0ull;	// ready for the next round
+	}
+	__syncthreads();
+	sort_keys_desc(keys, kPredictGroups);
+	if (F.parallel_src > 1) {
+		// group maxima can hide the 2nd .. P-th largest key behind a larger one of the same group: the exact pass
+		// (predict_exact_kernel) collects every key >= T = the P-th largest group maximum and finishes the round
+		if (threadIdx.x == 0) {
+			F.exact[0] = keys[F.parallel_src - 1];
+			F.exact[1] = 0ull;
+			*F.ticket = 0u;
+		}
+		if (threadIdx.x < kMaxRows) F.exact[2 + kExactCap + threadIdx.x] = keys[threadIdx.x];
+		return;
+	}
+	predict_finish(S, F, keys, cs);
+}
+
+// -parallel_src P > 1, second pass of the selection: every key >= T (the P-th largest group maximum; T = 0: every
+// candidate) is collected; the true P largest keys are among them.  The last CTA sorts the collected keys, appends the
+// group maxima below T (they only serve as speculative candidates) and finishes the round like predict_kernel does.
+__global__ void __launch_bounds__(1024) predict_exact_kernel(DevScene S, FastState F) {
+	__shared__ bool s_last;
+	const int T = gridDim.x * blockDim.x;
+	const unsigned long long thr = F.exact[0];
+	unsigned long long *list = F.exact + 2;
+	const int lane = threadIdx.x & 31;
+	for (int r0 = blockIdx.x * blockDim.x; r0 < S.R; r0 += T) {	// uniform trip count per CTA: warp votes inside
+		const int r = r0 + threadIdx.x;
+		unsigned long long k = 0ull;
+		if (r < S.R) {
+			unsigned c;
+			k = candidate_key(S, S.st[0][r].w, S.st[1][r].w, S.st[2][r].w, __ldg(&S.slot[r]), ~0ull, &c);
+		}
+		const bool take = k != 0ull && k >= thr;
+		const unsigned ball = __ballot_sync(0xffffffffu, take);
+		if (ball) {
+			unsigned long long pos = 0ull;
+			if (lane == 0) pos = atomicAdd(&F.exact[1], (unsigned long long)__popc(ball));
+			pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(ball & ((1u << lane) - 1u));
+			if (take && pos < (unsigned long long)kExactCap) list[pos] = k;
+		}
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = (atomicAdd(F.ticket, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	__shared__ unsigned long long keys[kExactCap];
+	__shared__ CacheScratch cs;
+	const unsigned long long m64 = __ldcg(&F.exact[1]);
+	if (m64 > (unsigned long long)kExactCap) {
+		// more keys above the threshold than the pass can sort (thousands of receivers hiding behind < P group maxima):
+		// fail loudly instead of selecting inexactly
+		if (threadIdx.x == 0) *F.error = 2, *F.ntodo = 0, *F.ticket = 0u, *F.local_count = 0u;
+		return;
+	}
+	const int m = (int)m64;
+	for (int q = threadIdx.x; q < kExactCap; q += blockDim.x) keys[q] = q < m ? __ldcg(&list[q]) : 0ull;
+	__syncthreads();
+	sort_keys_desc(keys, kExactCap);
+	// group maxima below the threshold follow (the sorted group maxima are descending; those >= T are already in the list)
+	if (threadIdx.x == 0 && thr != 0ull) {
+		int n = m;
+		const unsigned long long *gm = F.exact + 2 + kExactCap;
+		for (int q = 0; q < kMaxRows && n < kMaxRows; q++) {
+			const unsigned long long g = gm[q];
+			if (g != 0ull && g < thr) keys[n++] = g;
+		}
+	}
+	__syncthreads();
+	predict_finish(S, F, keys, cs);
 }
 
 // Multi-GPU second half of the prediction (one CTA of 1024 threads): wait for every rank's candidates,
@@ -372,6 +464,9 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 		}
 		*F.handoff = h;
 		F.counters[0] += (unsigned long long)nt, F.counters[1]++;
+		long long count = 0;
+		for (int t = 0; t < F.world; t++) count += (long long)*((volatile int *)&mine->pred[par][t][0].pad[1]);
+		*F.cand_count = count;
 	}
 	// adopt the shooter records of the new rows from the mailbox (one warp per row, 4-byte granules)
 	for (int t = warp; t < nt; t += (int)(blockDim.x >> 5)) {
@@ -631,53 +726,79 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 		}
 		key[c] = valid ? energy_key(S.converge, a0[c].w, a1[c].w, a2[c].w, slot[c]) : 0ull;
 	}
-	const long long budget = *F.budget;
-	const int kmax = (int)(budget < (long long)kMaxChain ? (budget < 0 ? 0 : budget) : (long long)kMaxChain);
-	auto lane_best = [&]() {
-		unsigned long long m = 0ull;
+	// One iteration of the reference's loop = n co-shooters (n = 1 without -parallel_src): the n largest keys, in
+	// descending order (the sequential restatement is chain_schedule_host in shot_core.cuh).
+	__shared__ ShotSched s_it[kMaxSources];
+	const int P = F.parallel_src;
+	long long lb = P > 1 ? *F.cand_count : 0ll;	// |C|: exact for the first iteration, a lower bound afterwards
+	const long long budget = *F.budget;		// iterations this step may still run
+	int k = 0, iters = 0, last = -1;
+	for (;;) {
+		if ((long long)iters >= budget) break;
+		if (iters > 0 && !shooter_count_certain(lb, P)) break;
+		const int n = P <= 1 ? 1 : shooters_for(lb, P);
+		if (n <= 0 || k + n > kMaxChain) break;
+		unsigned sel = 0u;	// bit c: my candidate c shoots in this iteration
+		unsigned long long minkey = 0ull;
+		bool ok = true;
+		for (int j = 0; j < n; j++) {
+			unsigned long long m = 0ull;
 #pragma unroll
-		for (int c = 0; c < kChainPerLane; c++) m = key[c] > m ? key[c] : m;
-		return m;
-	};
-	unsigned long long best = warp_max_u64(lane_best());
-	int k = 0;
-	while (best != 0ull && k < kmax) {
-		// the shooter: the lane that holds the best key (keys carry the slot, so non-zero keys are unique) and which of its candidates
-		int mine_c = -1;
+			for (int c = 0; c < kChainPerLane; c++)
+				if (!((sel >> c) & 1u) && key[c] > m) m = key[c];
+			const unsigned long long best = warp_max_u64(m);
+			if (best == 0ull) { ok = false; break; }	// the candidates cannot supply n shooters (uniform)
+			// the shooter: the lane that holds the best key (keys carry the slot, so non-zero keys are unique) and which of its candidates
+			int mine_c = -1;
 #pragma unroll
-		for (int c = 0; c < kChainPerLane; c++)
-			if (key[c] == best) mine_c = c;
-		const int bl = __ffs(__ballot_sync(0xffffffffu, mine_c >= 0)) - 1;
-		float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-		int ss = -1;
+			for (int c = 0; c < kChainPerLane; c++)
+				if (!((sel >> c) & 1u) && key[c] == best) mine_c = c;
+			if (mine_c >= 0) {
+				sel |= 1u << mine_c;
+				ShotSched e;
+				e.slot = -1, e.row = lane + 32 * mine_c;	// the shooter's candidate index = its cache row
+				e.dB[0] = e.dB[1] = e.dB[2] = 0.f;
 #pragma unroll
-		for (int c = 0; c < kChainPerLane; c++)
-			if (c == mine_c) d0 = a0[c].w, d1 = a1[c].w, d2 = a2[c].w, ss = slot[c];
-		const int bc = __shfl_sync(0xffffffffu, mine_c, bl);
-		const int b = bl + 32 * bc;	// the shooter's candidate index = its cache row
-		const int sslot = __shfl_sync(0xffffffffu, ss, bl);
-		const float sd0 = __shfl_sync(0xffffffffu, d0, bl), sd1 = __shfl_sync(0xffffffffu, d1, bl), sd2 = __shfl_sync(0xffffffffu, d2, bl);
+				for (int c = 0; c < kChainPerLane; c++)
+					if (c == mine_c) e.slot = slot[c], e.dB[0] = a0[c].w, e.dB[1] = a1[c].w, e.dB[2] = a2[c].w;
+				e.flags = (j == 0 ? kSchedHead : 0) | (j == n - 1 ? kSchedLast : 0);
+				e.next_key = 0ull;
+				s_it[j] = e;
+			}
+			minkey = best;
+		}
+		if (!ok) break;
+		__syncwarp();
+		if (last >= 0 && lane == 0) F.sched[last].next_key = minkey;
+		for (int j = lane; j < n; j += 32) F.sched[k + j] = s_it[j];
 #pragma unroll
 		for (int c = 0; c < kChainPerLane; c++) {
 			if (slot[c] < 0) continue;
-			if (slot[c] == sslot) a0[c].w = a1[c].w = a2[c].w = 0.0f;	// rad.cpp:446-449
-			else if (unsaturated(a0[c], a1[c], a2[c])) {
-				const float *f = cm[lane + 32 * c].fsum[b];
-				apply_shot_ff(a0[c], a1[c], a2[c], fkx[c], fky[c], fkz[c], f[0], f[1], f[2], sd0, sd1, sd2);
+			if ((sel >> c) & 1u) {	// rad.cpp:421-422: co-shooters do not receive; 446-449: their unshot energy is spent
+				a0[c].w = a1[c].w = a2[c].w = 0.0f;
+			} else if (unsaturated(a0[c], a1[c], a2[c])) {	// rad.cpp:424-428: once per iteration
+				for (int j = 0; j < n; j++) {
+					const float *f = cm[lane + 32 * c].fsum[s_it[j].row];
+					apply_shot_ff(a0[c], a1[c], a2[c], fkx[c], fky[c], fkz[c], f[0], f[1], f[2], s_it[j].dB[0], s_it[j].dB[1], s_it[j].dB[2]);
+				}
 			}
 			key[c] = energy_key(S.converge, a0[c].w, a1[c].w, a2[c].w, slot[c]);
 		}
-		best = warp_max_u64(lane_best());
-		if (lane == 0) {
-			ShotSched s;
-			s.slot = sslot, s.row = b, s.dB[0] = sd0, s.dB[1] = sd1, s.dB[2] = sd2, s.pad = 0, s.next_key = best;
-			F.sched[k] = s;
-		}
-		k++;
+		__syncwarp();	// s_it is rewritten by the next iteration; the entries' stores are ordered before the next_key patch
+		last = k + n - 1;
+		k += n, iters++, lb -= n;
+	}
+	{
+		// key of the shooter that would come next if the round went on (nothing scheduled follows: the test it feeds is harmless)
+		unsigned long long m = 0ull;
+#pragma unroll
+		for (int c = 0; c < kChainPerLane; c++) m = key[c] > m ? key[c] : m;
+		const unsigned long long best = warp_max_u64(m);
+		if (lane == 0 && last >= 0) F.sched[last].next_key = P <= 1 ? best : ~0ull;
 	}
 	if (lane == 0) {
 		*F.nsched = k, *F.viol = k, *F.apply_ticket = 0u;
-		F.counters[2] += (unsigned long long)k;
+		F.counters[2] += (unsigned long long)iters;
 	}
 }
 
@@ -721,14 +842,25 @@ __global__ void __launch_bounds__(kApplyBlock) apply_kernel(DevScene S, FastStat
 		__syncthreads();
 		n = s_n;
 		if (blockIdx.x == 0) {	// bookkeeping of the round (rad.cpp:504-514: loop counter; shot log for the tests)
+			// an iteration counts once and logs its first shooter (n ends an iteration: violations are reported on last entries)
+			__shared__ int s_iters;
 			const long long before = *S.sel.shots_done;
-			for (int k = threadIdx.x; k < n; k += kApplyBlock) S.sel.shot_log[(before + k) % S.sel.shot_log_cap] = F.sched[k].slot;
+			if (F.parallel_src <= 1) {
+				for (int k = threadIdx.x; k < n; k += kApplyBlock) S.sel.shot_log[(before + k) % S.sel.shot_log_cap] = F.sched[k].slot;
+				if (threadIdx.x == 0) s_iters = n;
+			} else if (threadIdx.x == 0) {
+				int it = 0;
+				for (int k = 0; k < n; k++)
+					if (F.sched[k].flags & kSchedHead) S.sel.shot_log[(before + it++) % S.sel.shot_log_cap] = F.sched[k].slot;
+				s_iters = it;
+			}
 			__syncthreads();
 			if (threadIdx.x == 0) {
-				*S.sel.shots_done = before + n;
-				*F.budget -= n;
-				atomicAdd(&S.stats->shots, (unsigned long long)n);
-				F.counters[3] += (unsigned long long)n;
+				const int it = s_iters;
+				*S.sel.shots_done = before + it;
+				*F.budget -= it;
+				atomicAdd(&S.stats->shots, (unsigned long long)it);
+				F.counters[3] += (unsigned long long)it;
 				if (n < K) F.counters[4]++;
 				// device-side round loop (CUDA graph while node): another round unless converged, out of budget or failed
 				if (F.cond) {

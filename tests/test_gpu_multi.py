@@ -74,6 +74,32 @@ def test_sharded_ranks_with_wide_candidate_sets(hr, models_dir):
         assert np.array_equal(dB[own].view(np.uint32), dB1[own].view(np.uint32))
 
 
+@pytest.mark.parametrize("name,P,world", [("sbox", 4, 2), ("model3s", 10, 3)])
+def test_sharded_ranks_with_parallel_sources(hr, models_dir, name, P, world):
+    """-parallel_src across ranks: every rank mails its exact local top P and its part of |C|; the merged schedule
+    and the results equal one GPU's generic multi-source kernel (itself pinned to the reference goldens)."""
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    one = hr.Context(m, parallel_src=P, per_shot_kernels=1)
+    done1, conv1 = one.step(-1)
+    acc1, dB1, _ = one.download()
+    ctxs = [hr.Context(m, opts=hr.default_opts(rank=r, world=world, parallel_src=P)) for r in range(world)]
+    hr.Context.connect_local(ctxs)
+    res = [None] * world
+
+    def work(r):
+        res[r] = ctxs[r].step(-1)
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert not any(t.is_alive() for t in th), "a rank hung"
+    for r, c in enumerate(ctxs):
+        assert res[r] == (done1, conv1) and c.shooter_log() == one.shooter_log()
+        own = c.owned_slots()
+        acc, dB, _ = c.download()
+        assert np.array_equal(acc[own].view(np.uint32), acc1[own].view(np.uint32))
+        assert np.array_equal(dB[own].view(np.uint32), dB1[own].view(np.uint32))
+
+
 def test_sharded_steps_in_pieces_and_rewind(hr, models_dir):
     m = hr.Model(str(models_dir / "model3s.tri"))
     one = hr.Context(m, per_shot_kernels=1)

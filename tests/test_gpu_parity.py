@@ -225,6 +225,44 @@ def test_multi_source_matches_golden(hr, golden, models_dir):
         assert d["accB_sha"] == g["accB_sha"] and d["deltaB_sha"] == g["deltaB_sha"], vname
 
 
+def test_multi_source_batched_path_matches_golden(hr, golden, models_dir):
+    """-parallel_src on the default (batched) path: exact top-P selection pass, iterations of co-shooters in the chained
+    schedule.  Same iterations, same bits as the unmodified reference (the reference's own go.sh configuration: room_go)."""
+    for vname, rows in [("sbox_src4", 0), ("sbox_src4", 8), ("room_go", 0)]:
+        g = golden["variants"][vname]
+        kw = {"tri_limit": 40000} if vname == "room_go" else {}
+        m = hr.Model(str(models_dir / f"{g['model']}.tri"), **kw)
+        P = int(g["argv"][g["argv"].index("-parallel_src") + 1])
+        ctx = hr.Context(m, opts=hr.default_opts(parallel_src=P, ff_rows=rows))
+        done, conv = ctx.step(-1)
+        assert conv and done == g["shots"], (vname, done, g["shots"])
+        assert ctx.stats()["rounds"] > 0                # the batched path ran
+        ctx.download_into(m)
+        d = state_digest(m.triangles)
+        assert d["accB_sha"] == g["accB_sha"] and d["deltaB_sha"] == g["deltaB_sha"], vname
+        assert ctx.shooter_log() == [x[0] for x in g["shooters"]]   # first shooter of every iteration
+
+
+def test_multi_source_batched_path_in_pieces(hr, po, models_dir):
+    """Stepping with a budget (iterations, like the reference's loop counter and -write_cycle) and 50 co-shooters."""
+    m = hr.Model(str(models_dir / "model3s.tri"))
+    for P, pieces in [(6, [1, 3, 7, -1]), (50, [2, -1])]:
+        sc = oracle_scene(po, m, parallel_src=P)
+        seq = sc.run(None)
+        ctx = hr.Context(m, parallel_src=P)
+        total = 0
+        for k in pieces:
+            done, conv = ctx.step(k)
+            total += done
+            assert done == k or k < 0 or conv
+        assert conv and total == len(seq)
+        assert ctx.shooter_log() == [x[0] for x in seq]
+        acc, dB, par = ctx.download()
+        live = sc.slots["parent"] >= 0
+        assert np.array_equal(acc[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
+        assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
+
+
 def test_light_and_converge_options(hr, golden, models_dir):
     g = golden["variants"]["church_light05"]
     m = hr.Model(str(models_dir / "church.tri"), light=0.5)
