@@ -273,13 +273,10 @@ RADK_HD bool entry_gives_nan(const DevTree &T, int entry, float px, float py, fl
 	return t != t;
 }
 
-// 0: nothing accepted under the bound, 1: some entry accepted (blocker) and no entry of the list gives a NaN t,
-// 2: an entry gives a NaN t (before or after the first blocker): the reference's answer then depends on the scan order
-// (a NaN t_min accepts every later entry, raycast.cpp:300,323-328), and the caller runs the sequential scan instead.
-RADK_HD int leaf_any_hit_bounded(const DevTree &T, int list4_off, float px, float py, float pz, float vx, float vy, float vz,
-				 int ban, float t_max, int tie) {
+// Does any entry of the padded list with index below `below` give a NaN t for this ray?
+RADK_HD bool list_gives_nan_below(const DevTree &T, int list4_off, int below, float px, float py, float pz, float vx, float vy, float vz,
+				  int ban) {
 	const int4 *l4 = T.list4 + list4_off;
-	bool blocked = false;
 	for (;;) {
 		const int4 id = ldg(l4++);
 		const int e[4] = {id.x, id.y, id.z, id.w};
@@ -287,14 +284,8 @@ RADK_HD int leaf_any_hit_bounded(const DevTree &T, int list4_off, float px, floa
 #pragma unroll
 #endif
 		for (int k = 0; k < 4; k++) {
-			if (e[k] < 0) return blocked ? 1 : 0;
-			if (!blocked) {
-				const int r = any_hit_bounded_one(T, e[k], px, py, pz, vx, vy, vz, ban, t_max, tie);
-				if (r == 2) return 2;
-				blocked = r == 1;
-			} else if (entry_gives_nan(T, e[k], px, py, pz, vx, vy, vz, ban)) {
-				return 2;
-			}
+			if (e[k] < 0) return false;
+			if ((e[k] & kIdMask) < below && entry_gives_nan(T, e[k], px, py, pz, vx, vy, vz, ban)) return true;
 		}
 	}
 }
@@ -317,26 +308,56 @@ int leaf_visit_exact(const int *lp, const float4 *occ, int nocc, float px, float
 	return hit < 0 ? -1 : (hit == logsrc);
 }
 
+// leaf_visit() met a blocker (nan_idx < 0) or a NaN entry (nan_idx = its index) in a leaf whose logsrc passes: 0 unless a
+// NaN entry below logsrc may have revived it - then the reference's sequential scan decides.  Out of line: registers of
+// the hot scan.
+RADK_HD int leaf_visit_rare(const DevTree &T, int cur, int nan_idx, float px, float py, float pz, float vx, float vy, float vz, int ban, int logsrc) {
+	if (nan_idx >= 0 ? nan_idx > logsrc : !list_gives_nan_below(T, ldg(&T.leaf_list4[cur]), logsrc, px, py, pz, vx, vy, vz, ban)) return 0;
+	return leaf_visit_exact(T.list + float_as_int_hd(leaf_lo(T, cur).w), T.occ, T.nocc, px, py, pz, vx, vy, vz, ban, logsrc);
+}
+
 // One leaf visit of a shooter-visibility ray: -1 nothing hit here (walk on), 0 the walk ends on another
 // triangle, 1 the walk ends on logsrc.  Same answer as TriListHitted(...) compared with logsrc.
+//
+// NaN: an entry whose plane contains the ray (a1 == a2 == 0, t = 0/0) passes every test of TriHitted, leaves t_min = NaN
+// and with it every later passing entry is accepted whatever its t (raycast.cpp:300,323-328); the lists are ascending,
+// so "later" = larger triangle index.  Church has many such rays (vertices on a crease, shot along the adjoining wall).
+// What the scan below relies on, with `passes` = t >= 0.0001 and the inside test, no bound on t:
+//   * a NaN entry is always accepted: a leaf with one ends the walk;
+//   * the walk can only end on logsrc if logsrc is listed, is not the banned triangle and passes, and then only if
+//     no NaN entry has a larger index;
+// so a NaN entry or a blocker met while logsrc does not pass means "ends elsewhere" without looking further, a NaN
+// entry above logsrc too, and a blocker stands unless some NaN entry lies below logsrc.  Whatever is left (a NaN entry
+// below a passing logsrc) takes the reference's sequential scan.
 RADK_HD int leaf_visit(const DevTree &T, int cur, bool lists_src, float px, float py, float pz, float vx, float vy, float vz,
 		       int ban, int logsrc, bool exact = false) {
 	// exact: take the reference's sequential scan unconditionally (tests: the two scans must agree on every ray)
 	if (exact) return leaf_visit_exact(T.list + float_as_int_hd(leaf_lo(T, cur).w), T.occ, T.nocc, px, py, pz, vx, vy, vz, ban, logsrc);
-	float t_max = 1000000.0f;
+	// (t_max, tie): the bound of the any-hit scan.  tie >= 0 <=> logsrc is listed, not banned, passes and has t < 1e6.
+	float t_max = int_as_float_hd(0x7fc00000);	// NaN: no bound at all for the source itself (`passes` above; even t = +inf passes once t_min is NaN)
 	int tie = -1;
-	bool src_hit = false;
-	if (lists_src && logsrc != ban) {
-		src_hit = tri_hit(occ_plane(T, logsrc), occ_side(T, logsrc), px, py, pz, vx, vy, vz, t_max);
-		if (src_hit) tie = logsrc;
+	if (lists_src && logsrc != ban && tri_hit(occ_plane(T, logsrc), occ_side(T, logsrc), px, py, pz, vx, vy, vz, t_max)) {
+		if (!(t_max < 1000000.0f))	// t NaN, infinite or beyond the reference's initial t_min = 1e6 (rays inside the source's plane): sequential scan
+			return leaf_visit_exact(T.list + float_as_int_hd(leaf_lo(T, cur).w), T.occ, T.nocc, px, py, pz, vx, vy, vz, ban, logsrc);
+		tie = logsrc;
+	} else {
+		t_max = 1000000.0f;
 	}
-	int r = (t_max != t_max) ? 2 : leaf_any_hit_bounded(T, ldg(&T.leaf_list4[cur]), px, py, pz, vx, vy, vz, ban, t_max, tie);
-	if (r == 2) {
-		if (!lists_src) return 0;	// without logsrc in the list any acceptance (a NaN t is one) ends the walk elsewhere
-		return leaf_visit_exact(T.list + float_as_int_hd(leaf_lo(T, cur).w), T.occ, T.nocc, px, py, pz, vx, vy, vz, ban, logsrc);
+	const int4 *l4 = T.list4 + ldg(&T.leaf_list4[cur]);
+	for (;;) {
+		const int4 id = ldg(l4++);
+		const int e[4] = {id.x, id.y, id.z, id.w};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int k = 0; k < 4; k++) {
+			if (e[k] < 0) return tie >= 0 ? 1 : -1;
+			const int r = any_hit_bounded_one(T, e[k], px, py, pz, vx, vy, vz, ban, t_max, tie);
+			if (r == 0) continue;
+			if (tie < 0) return 0;	// accepted (blocker or NaN entry) while logsrc does not pass: the walk ends here, and not on logsrc
+			return leaf_visit_rare(T, cur, r == 2 ? (e[k] & kIdMask) : -1, px, py, pz, vx, vy, vz, ban, logsrc);
+		}
 	}
-	if (r == 1) return 0;
-	return src_hit ? 1 : -1;
 }
 
 // Is the shooter visible?  Same answer as (ray_walk(...) == logsrc); the walk of ff_batch_kernel.

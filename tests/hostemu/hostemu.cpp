@@ -250,7 +250,7 @@ extern "C" int emu_start_block_stats(const radk_scene *s, int shooter_slot, long
 				if (sees) return 2;	// the criterion must never kill a visible ray
 			}
 			if (leaf >= 0 && !((mask[leaf >> 5] >> (leaf & 31)) & 1u) && !sees) {
-				if (leaf_any_hit_bounded(T, F.leaf_list4[leaf], v.x, v.y, v.z, dx, dy, dz, par, 1000000.0f, -1)) first_leaf_blocked++;
+				if (leaf_visit(T, leaf, false, v.x, v.y, v.z, dx, dy, dz, par, sh.logsrc) == 0) first_leaf_blocked++;
 			}
 		}
 	}
