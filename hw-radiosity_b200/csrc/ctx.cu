@@ -236,8 +236,13 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	chain_kernel<<<1, 256, chain_smem_bytes(c->rows), st>>>(c->S, F);
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
-	apply_kernel<false><<<nb, kApplyBlock, 0, st>>>(c->S, F);
-	apply_kernel<true><<<nb, kApplyBlock, 0, st>>>(c->S, F);
+	if (c->F.parallel_src > 1) {
+		apply_kernel<false, true><<<nb, kApplyBlock, 0, st>>>(c->S, F);
+		apply_kernel<true, true><<<nb, kApplyBlock, 0, st>>>(c->S, F);
+	} else {
+		apply_kernel<false, false><<<nb, kApplyBlock, 0, st>>>(c->S, F);
+		apply_kernel<true, false><<<nb, kApplyBlock, 0, st>>>(c->S, F);
+	}
 	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
 	c->launches += 5;
 	return RADK_OK;
@@ -270,8 +275,13 @@ bool build_loop_graph(radk_ctx *c) {
 	if (c->F.world > 1) ks.push_back({(const void *)predict_merge_kernel, dim3(1), dim3(1024), 0});
 	ks.push_back({(const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock), 0});
 	ks.push_back({(const void *)chain_kernel, dim3(1), dim3(256), chain_smem_bytes(c->rows)});
-	ks.push_back({(const void *)apply_kernel<false>, dim3(nb), dim3(kApplyBlock), 0});
-	ks.push_back({(const void *)apply_kernel<true>, dim3(nb), dim3(kApplyBlock), 0});
+	if (c->F.parallel_src > 1) {
+		ks.push_back({(const void *)apply_kernel<false, true>, dim3(nb), dim3(kApplyBlock), 0});
+		ks.push_back({(const void *)apply_kernel<true, true>, dim3(nb), dim3(kApplyBlock), 0});
+	} else {
+		ks.push_back({(const void *)apply_kernel<false, false>, dim3(nb), dim3(kApplyBlock), 0});
+		ks.push_back({(const void *)apply_kernel<true, false>, dim3(nb), dim3(kApplyBlock), 0});
+	}
 	cudaGraphNode_t prev = nullptr;
 	bool ok = true;
 	for (auto &k : ks) {

@@ -858,9 +858,18 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 // in st_prev, writes the state after all scheduled shots, reports the first violation).  COMMIT = true: after the
 // first violation is known - re-applies the valid prefix from st_prev if the schedule went further, and does the
 // round's bookkeeping.
-constexpr int kApplyBlock = 256;
-template <bool COMMIT>
-__global__ void __launch_bounds__(kApplyBlock) apply_kernel(DevScene S, FastState F) {
+// 128 threads x 7 CTAs per SM (72 registers): 896 receivers per SM in flight, so a church-sized shard (116 791 receivers,
+// 789 per SM) is ONE wave; with 256 x 3 (80 registers, 768 per SM) a second, nearly empty wave doubled the pass
+// (measured church update 0.87 -> 0.77 ms; 256 x 4: 0.82, 128 x 6: 0.84; box / room unchanged)
+#ifndef RADK_APPLY_BLOCK
+#define RADK_APPLY_BLOCK 128
+#endif
+#ifndef RADK_APPLY_MINB
+#define RADK_APPLY_MINB 7
+#endif
+constexpr int kApplyBlock = RADK_APPLY_BLOCK;
+template <bool COMMIT, bool MULTI>	// MULTI: -parallel_src > 1 (iterations with co-shooters)
+__global__ void __launch_bounds__(kApplyBlock, RADK_APPLY_MINB) apply_kernel(DevScene S, FastState F) {
 	__shared__ ShotSched sched[kMaxChain];
 	__shared__ int s_n, s_wmin[kApplyBlock / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -897,7 +906,7 @@ __global__ void __launch_bounds__(kApplyBlock) apply_kernel(DevScene S, FastStat
 			// an iteration counts once and logs its first shooter (n ends an iteration: violations are reported on last entries)
 			__shared__ int s_iters;
 			const long long before = *S.sel.shots_done;
-			if (F.parallel_src <= 1) {
+			if (!MULTI) {
 				for (int k = threadIdx.x; k < n; k += kApplyBlock) S.sel.shot_log[(before + k) % S.sel.shot_log_cap] = F.sched[k].slot;
 				if (threadIdx.x == 0) s_iters = n;
 			} else if (threadIdx.x == 0) {
@@ -939,7 +948,8 @@ __global__ void __launch_bounds__(kApplyBlock) apply_kernel(DevScene S, FastStat
 		const int4 id = __ldg(&S.vid[r]);
 		const int slot = __ldg(&S.slot[r]);
 		const float4 fk = __ldg(&S.par_fk[id.w]);
-		viol = apply_schedule(a0, a1, a2, id.x, id.y, id.z, fk.x, fk.y, fk.z, slot, sched, n, S.converge, FFRows{F.ff, S.U});
+		if (MULTI) viol = apply_schedule_multi(a0, a1, a2, id.x, id.y, id.z, fk.x, fk.y, fk.z, slot, sched, n, S.converge, FFRows{F.ff, S.U});
+		else viol = apply_schedule_single(a0, a1, a2, id.x, id.y, id.z, fk.x, fk.y, fk.z, slot, sched, n, S.converge, FFRows{F.ff, S.U});
 		S.st[0][r] = a0, S.st[1][r] = a1, S.st[2][r] = a2;
 	}
 	if (COMMIT) return;

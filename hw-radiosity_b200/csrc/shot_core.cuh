@@ -179,7 +179,7 @@ inline int chain_schedule_host(CandRec *c, int rows, float converge, long long m
 // iteration after which the schedule no longer holds for this receiver (n: none): its key exceeds next_key, or it left
 // the candidate set without shooting (a NaN energy; the chain's lower bound on |C| would be wrong).
 template <typename FF>
-RADK_HD int apply_schedule(float4 &a0, float4 &a1, float4 &a2, int id0, int id1, int id2, float fkx, float fky, float fkz,
+RADK_HD int apply_schedule_multi(float4 &a0, float4 &a1, float4 &a2, int id0, int id1, int id2, float fkx, float fky, float fkz,
 			   int slot, const ShotSched *sched, int n, float converge, FF ff) {
 	int viol = n;
 	// the form factors of a shot do not depend on the receiver's state: those of kChunk shots are fetched together
@@ -218,6 +218,46 @@ RADK_HD int apply_schedule(float4 &a0, float4 &a1, float4 &a2, int id0, int id1,
 		}
 	}
 	return viol;
+}
+
+// Single shooter per iteration (no -parallel_src): every entry is an iteration of its own.
+template <typename FF>
+RADK_HD int apply_schedule_single(float4 &a0, float4 &a1, float4 &a2, int id0, int id1, int id2, float fkx, float fky, float fkz,
+				  int slot, const ShotSched *sched, int n, float converge, FF ff) {
+	int viol = n;
+	constexpr int kChunk = 8;
+	for (int k0 = 0; k0 < n; k0 += kChunk) {
+		float f[kChunk][3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int j = 0; j < kChunk; j++) {
+			const int row = sched[k0 + j < n ? k0 + j : n - 1].row;
+			f[j][0] = ff(row, id0), f[j][1] = ff(row, id1), f[j][2] = ff(row, id2);
+		}
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int j = 0; j < kChunk; j++) {
+			const int k = k0 + j;
+			if (k >= n) break;
+			const ShotSched &s = sched[k];
+			if (slot == s.slot) {
+				a0.w = a1.w = a2.w = 0.0f;
+			} else if (unsaturated(a0, a1, a2)) {
+				apply_shot_ff(a0, a1, a2, fkx, fky, fkz, f[j][0], f[j][1], f[j][2], s.dB[0], s.dB[1], s.dB[2]);
+			}
+			if (viol == n && energy_key(converge, a0.w, a1.w, a2.w, slot) > s.next_key) viol = k;
+		}
+	}
+	return viol;
+}
+
+template <typename FF>
+RADK_HD int apply_schedule(float4 &a0, float4 &a1, float4 &a2, int id0, int id1, int id2, float fkx, float fky, float fkz,
+			   int slot, const ShotSched *sched, int n, float converge, FF ff, bool multi = true) {
+	return multi ? apply_schedule_multi(a0, a1, a2, id0, id1, id2, fkx, fky, fkz, slot, sched, n, converge, ff)
+		     : apply_schedule_single(a0, a1, a2, id0, id1, id2, fkx, fky, fkz, slot, sched, n, converge, ff);
 }
 
 }  // namespace radk

@@ -438,7 +438,7 @@ extern "C" int emu_shard_apply(void *h) {
 		const int4 id = F.vid[r];
 		const float4 fk = F.par_fk[id.w];
 		const int v1 = apply_schedule(F.st[0][r], F.st[1][r], F.st[2][r], id.x, id.y, id.z, fk.x, fk.y, fk.z, F.recv_slot[r], e->sched,
-					      e->nsched, e->converge, ffa);
+					      e->nsched, e->converge, ffa, e->parallel_src > 1);
 		viol = std::min(viol, v1);
 	}
 	return viol;
@@ -456,7 +456,7 @@ extern "C" int emu_shard_commit(void *h, int viol, int *slots) {
 			for (int v = 0; v < 3; v++) F.st[v][r] = e->prev[v][r];
 			const int4 id = F.vid[r];
 			const float4 fk = F.par_fk[id.w];
-			apply_schedule(F.st[0][r], F.st[1][r], F.st[2][r], id.x, id.y, id.z, fk.x, fk.y, fk.z, F.recv_slot[r], e->sched, n, e->converge, ffa);
+			apply_schedule(F.st[0][r], F.st[1][r], F.st[2][r], id.x, id.y, id.z, fk.x, fk.y, fk.z, F.recv_slot[r], e->sched, n, e->converge, ffa, e->parallel_src > 1);
 		}
 		e->reapplied++;
 	}
