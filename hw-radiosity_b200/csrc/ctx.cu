@@ -103,6 +103,10 @@ struct radk_ctx {
 	DevBuf<int> fast_error;
 	DevBuf<unsigned long long> exact;	// -parallel_src: threshold, list length, collected keys, sorted group maxima
 	DevBuf<long long> cand_count;
+	DevBuf<float2> cand_ff;
+	cudaStream_t side = nullptr;		// ff_cand_kernel + chain_kernel run here, beside ff_batch_kernel (host-launched rounds)
+	bool overlap = true;			// false: ranks share this device (tests) - one stream per rank, see radk_ctx_peer_connect_local
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	DevBuf<unsigned long long> dbg;
 	std::vector<void *> ipc_opened;
 	bool peers_connected = false;
@@ -231,10 +235,24 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	if (c->F.parallel_src > 1) { predict_exact_kernel<<<64, 1024, 0, st>>>(c->S, F); c->launches++; }
 	if (c->F.world > 1) { predict_merge_kernel<<<1, 1024, 0, st>>>(c->S, F); c->launches++; }
 	if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
+	// fork: the form factors of all vertices on the main stream; beside them the candidates' own form factors and
+	// the chain (a few thousand rays, then a single warp)
+	// the side stream exists only where it is used: every stream takes one of the device's few hardware queues, and
+	// ranks that share a device (tests) deadlock when a kernel waiting for a peer's mail is queued in front of the
+	// peer's kernel that sends it
+	if (c->overlap && !c->side) CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+	cudaStream_t sd = c->overlap ? c->side : st;
+	if (c->overlap) {
+		CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+		CUDA_TRY(cudaStreamWaitEvent(sd, c->ev_fork, 0));
+	}
+	ff_cand_kernel<<<dim3((unsigned)((c->rows * 6 + 127) / 128), (unsigned)c->rows), 128, 0, sd>>>(c->S, F);
+	chain_kernel<<<1, 256, chain_smem_bytes(c->rows), sd>>>(c->S, F);
+	if (c->overlap) CUDA_TRY(cudaEventRecord(c->ev_join, sd));
 	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
 	ff_batch_kernel<<<g, kFFBlock, 0, st>>>(c->S, F);
+	if (c->overlap) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-	chain_kernel<<<1, 256, chain_smem_bytes(c->rows), st>>>(c->S, F);
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
 	if (c->F.parallel_src > 1) {
 		apply_kernel<false, true><<<nb, kApplyBlock, 0, st>>>(c->S, F);
@@ -244,7 +262,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 		apply_kernel<true, false><<<nb, kApplyBlock, 0, st>>>(c->S, F);
 	}
 	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-	c->launches += 5;
+	c->launches += 6;
 	return RADK_OK;
 }
 
@@ -267,30 +285,39 @@ bool build_loop_graph(radk_ctx *c) {
 	cudaGraph_t body = cp.conditional.phGraph_out[0];
 	c->F.cond = (unsigned long long)h;
 	void *args[] = {(void *)&c->S, (void *)&c->F};
-	struct K { const void *fn; dim3 grid, block; size_t smem; };
+	struct K { const void *fn; dim3 grid, block; size_t smem; int dep0, dep1; };	// dep: index of a kernel this one waits for (-1: none)
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
 	std::vector<K> ks;
-	ks.push_back({(const void *)predict_kernel, dim3(64), dim3(1024), 0});
-	if (c->F.parallel_src > 1) ks.push_back({(const void *)predict_exact_kernel, dim3(64), dim3(1024), 0});
-	if (c->F.world > 1) ks.push_back({(const void *)predict_merge_kernel, dim3(1), dim3(1024), 0});
-	ks.push_back({(const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock), 0});
-	ks.push_back({(const void *)chain_kernel, dim3(1), dim3(256), chain_smem_bytes(c->rows)});
+	auto add = [&](const void *fn, dim3 grid, dim3 block, size_t smem, int dep0, int dep1 = -1) {
+		ks.push_back({fn, grid, block, smem, dep0, dep1});
+		return (int)ks.size() - 1;
+	};
+	int last = add((const void *)predict_kernel, dim3(64), dim3(1024), 0, -1);
+	if (c->F.parallel_src > 1) last = add((const void *)predict_exact_kernel, dim3(64), dim3(1024), 0, last);
+	if (c->F.world > 1) last = add((const void *)predict_merge_kernel, dim3(1), dim3(1024), 0, last);
+	// fork: the form factors of all vertices | the candidates' own form factors, then the chain (a single warp)
+	const int kcand = add((const void *)ff_cand_kernel, dim3((unsigned)((c->rows * 6 + 127) / 128), (unsigned)c->rows), dim3(128), 0, last);
+	const int kff = add((const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock), 0, last);
+	const int kchain = add((const void *)chain_kernel, dim3(1), dim3(256), chain_smem_bytes(c->rows), kcand);
 	if (c->F.parallel_src > 1) {
-		ks.push_back({(const void *)apply_kernel<false, true>, dim3(nb), dim3(kApplyBlock), 0});
-		ks.push_back({(const void *)apply_kernel<true, true>, dim3(nb), dim3(kApplyBlock), 0});
+		last = add((const void *)apply_kernel<false, true>, dim3(nb), dim3(kApplyBlock), 0, kff, kchain);
+		last = add((const void *)apply_kernel<true, true>, dim3(nb), dim3(kApplyBlock), 0, last);
 	} else {
-		ks.push_back({(const void *)apply_kernel<false, false>, dim3(nb), dim3(kApplyBlock), 0});
-		ks.push_back({(const void *)apply_kernel<true, false>, dim3(nb), dim3(kApplyBlock), 0});
+		last = add((const void *)apply_kernel<false, false>, dim3(nb), dim3(kApplyBlock), 0, kff, kchain);
+		last = add((const void *)apply_kernel<true, false>, dim3(nb), dim3(kApplyBlock), 0, last);
 	}
-	cudaGraphNode_t prev = nullptr;
+	std::vector<cudaGraphNode_t> nodes(ks.size());
 	bool ok = true;
-	for (auto &k : ks) {
+	for (size_t i = 0; i < ks.size(); i++) {
+		const K &k = ks[i];
 		cudaKernelNodeParams kp;
 		memset(&kp, 0, sizeof(kp));
 		kp.func = (void *)k.fn, kp.gridDim = k.grid, kp.blockDim = k.block, kp.sharedMemBytes = (unsigned)k.smem, kp.kernelParams = args, kp.extra = nullptr;
-		cudaGraphNode_t n;
-		if (cudaGraphAddKernelNode(&n, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp) != cudaSuccess) { ok = false; break; }
-		prev = n;
+		cudaGraphNode_t deps[2];
+		int nd = 0;
+		if (k.dep0 >= 0) deps[nd++] = nodes[k.dep0];
+		if (k.dep1 >= 0) deps[nd++] = nodes[k.dep1];
+		if (cudaGraphAddKernelNode(&nodes[i], body, nd ? deps : nullptr, nd, &kp) != cudaSuccess) { ok = false; break; }
 	}
 	cudaGraphExec_t exec = nullptr;
 	if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) ok = false;
@@ -546,6 +573,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		CUDA_TRY(c->fast_error.alloc(1));
 		CUDA_TRY(c->exact.alloc(2 + kExactCap + kMaxRows));
 		CUDA_TRY(c->cand_count.alloc(1));
+		CUDA_TRY(c->cand_ff.alloc((size_t)kMaxRows * kMaxRows * 3));
 		CUDA_TRY(cudaMemsetAsync(c->box.p, 0, sizeof(PeerBox), st));
 		const int mask_words = (s->nnodes + 31) / 32;
 		CUDA_TRY(c->row_mask.alloc((size_t)kMaxRows * mask_words));
@@ -563,6 +591,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.rank = o.rank, F.world = world;
 		F.pred_round = c->pred_round.p, F.error = c->fast_error.p;
 		F.parallel_src = P, F.local_count = c->fast_uints.p + 2, F.cand_count = c->cand_count.p, F.exact = c->exact.p;
+		F.cand_ff = c->cand_ff.p;
 		F.dbg = nullptr;
 		if (getenv("RADK_DEBUG_PREDICT")) { CUDA_TRY(c->dbg.alloc(16)); CUDA_TRY(cudaMemsetAsync(c->dbg.p, 0, 16 * 8, st)); F.dbg = c->dbg.p; }
 		c->peers_connected = world == 1;
@@ -651,7 +680,10 @@ int read_flags(radk_ctx *c) {
 	}
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if (c->use_fast && *c->h_error == 2) { set_error("-parallel_src selection: more than 2048 receivers above the selection threshold share fewer than P selection groups"); return RADK_ERR_LIMIT; }
-	if (c->use_fast && *c->h_error) { set_error("a peer rank did not answer within the device-side timeout"); return RADK_ERR_STATE; }
+	if (c->use_fast && *c->h_error) {
+		set_error("a peer rank did not answer within the device-side timeout (exchange " + std::to_string(*c->h_error) + ": 11 candidates, 12 candidate records, 13 first violation)");
+		return RADK_ERR_STATE;
+	}
 	return RADK_OK;
 }
 
@@ -682,6 +714,8 @@ int radk_ctx_create(const radk_scene *s, const radk_opts *o, radk_ctx **out) {
 	int rc = RADK_OK;
 	do {
 		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
 		    cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
 		    cudaMallocHost((void **)&c->h_flags, sizeof(*c->h_flags)) != cudaSuccess ||
 		    cudaMallocHost((void **)&c->h_shots, sizeof(long long)) != cudaSuccess ||
@@ -719,6 +753,9 @@ void radk_ctx_destroy(radk_ctx *c) {
 	for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
+	if (c->side) cudaStreamDestroy(c->side);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -1258,8 +1295,11 @@ int radk_ctx_peer_connect_local(radk_ctx *c, radk_ctx *const *peers, int world) 
 		}
 		if (t != c->opt.rank && peers[t]->device == c->device) {
 			// ranks that share a device (tests): graphs with device-side loops of two contexts do not overlap on one
-			// device, and each rank's kernels wait for the other's mail - launch the rounds from the host instead
+			// device, and each rank's kernels wait for the other's mail - launch the rounds from the host instead, and
+			// on ONE stream per rank: with more streams than hardware queues a kernel that waits for a peer's mail can
+			// end up queued in front of the peer's kernel that sends it
 			c->graph_tried = true;
+			c->overlap = false;
 		}
 		if (peers[t]->device != c->device) {
 			cudaError_t e = cudaDeviceEnablePeerAccess(peers[t]->device, 0);

@@ -89,6 +89,8 @@ struct FastState {
 	unsigned *apply_ticket;		// last-CTA-done counter of apply_kernel (multi-GPU: the last CTA mails viol)
 	float4 *st_prev[3];		// [R] the receivers' state before the round's apply pass
 	unsigned long long *counters;	// [8] 0: rows filled, 1: rounds, 2: shots scheduled, 3: shots committed, 4: rounds that re-applied
+	float2 *cand_ff;		// [kMaxRows new rows][kMaxRows candidates][3 vertices] form factors of this round's NEW rows at the
+					// candidates' vertices (ff_cand_kernel): lets chain_kernel run beside ff_batch_kernel
 	// -parallel_src P > 1 (an iteration shoots min((|C| + 4) / 5, P) patches, rad.cpp:387-404)
 	int parallel_src;
 	unsigned *local_count;		// receivers of this shard above the convergence limit, counted by predict_kernel's scan
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 	__syncthreads();
 	if (!s_ok) {
 		if (threadIdx.x == 0) {
-			*F.error = 1, *F.ntodo = 0;
+			*F.error = 11, *F.ntodo = 0;	// 11: the candidates of a rank did not arrive (or its cache size differs)
 			ShotRec h = {-1, -1, {0.f, 0.f, 0.f}, 0, {0, 0}};
 			*F.handoff = h;
 		}
@@ -609,6 +611,38 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 	}
 }
 
+// ---- form factors of the new rows at the candidates' own vertices ---------------------------------------
+// chain_kernel only needs the form factors between the candidates (a rows x rows x 3 table).  Those of rows cached
+// in earlier rounds are in the cache already; those of the rows this round fills are computed here, ray by ray
+// (at most rows x rows x 3 x 2 rays, the same arithmetic as ff_batch_kernel: ff_geom + the bounded any-hit walk),
+// so that the chain - a single warp - runs concurrently with ff_batch_kernel instead of after it.
+// grid (ceil(rows * 6 / 128), rows); thread = (candidate i, vertex v, half) of todo entry blockIdx.y.
+__global__ void __launch_bounds__(128) ff_cand_kernel(DevScene S, FastState F) {
+	const int t = blockIdx.y;
+	if (t >= *F.ntodo) return;
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = q / 6, v = (q % 6) >> 1, half = q & 1;
+	if (i >= F.rows) return;
+	const int cslot = F.row_slot[i];
+	const int r = cslot >= 0 ? S.slot_to_recv[cslot] : -1;
+	if (r < 0) return;	// free row, or a candidate another rank owns
+	const int row = F.todo[t];
+	const ShooterRec &sh = F.rec[row];
+	const int4 id = __ldg(&S.vid[r]);
+	const int u = v == 0 ? id.x : (v == 1 ? id.y : id.z);
+	float ff = 0.0f;
+	if (sh.splittable || half == 0) {
+		const FFSample &smp = sh.splittable ? sh.half[half] : sh.centre;
+		const float4 p = __ldg(&S.uv[u]);
+		const float4 pn = __ldg(&S.par_n[__float_as_int(p.w)]);
+		float dx, dy, dz;
+		bool cast;
+		const float g = ff_geom(smp, pn.x, pn.y, pn.z, pn.w, p.x, p.y, p.z, dx, dy, dz, cast);
+		if (cast && ray_sees(S.tree, F.row_mask + (size_t)row * F.mask_words, p.x, p.y, p.z, dx, dy, dz, __float_as_int(p.w), sh.logsrc)) ff = g;
+	}
+	((float *)&F.cand_ff[((size_t)t * kMaxRows + i) * 3 + v])[half] = ff;
+}
+
 // ---- chained shot loop ----------------------------------------------------------------------------
 // word of the per-round violation mail: run epoch (16 bits) | round (40 bits) | first violation (8 bits)
 __device__ __forceinline__ unsigned long long viol_word(unsigned long long round, int v) {	// round = epoch << 40 | round number
@@ -661,14 +695,31 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 		}
 	}
 	__syncthreads();
+	// rows filled in this round: ff_batch_kernel may still be writing them - their values at the candidates' vertices
+	// come from ff_cand_kernel's table (s_todo_of[row] = todo entry, -1 for rows cached earlier)
+	__shared__ int s_todo_of[kMaxRows];
+	for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) s_todo_of[i] = -1;
+	__syncthreads();
+	{
+		const int nt = *F.ntodo;
+		for (int t = threadIdx.x; t < nt; t += blockDim.x) s_todo_of[F.todo[t]] = t;
+	}
+	__syncthreads();
 	for (int q = threadIdx.x; q < rows * rows; q += blockDim.x) {	// (candidate i, row j)
 		const int i = q / rows, j = q - i * rows;
 		if (!s_owned[i]) continue;
 		const bool filled = s_filled[j];
 		const int4 id = s_id[i];
-		cm[i].fsum[j][0] = filled ? ff_sum(F.ff, S.U, j, id.x) : 0.0f;
-		cm[i].fsum[j][1] = filled ? ff_sum(F.ff, S.U, j, id.y) : 0.0f;
-		cm[i].fsum[j][2] = filled ? ff_sum(F.ff, S.U, j, id.z) : 0.0f;
+		const int t = s_todo_of[j];
+		if (t >= 0) {
+			const float2 *cf = F.cand_ff + ((size_t)t * kMaxRows + i) * 3;
+			const float2 h0 = __ldcg(&cf[0]), h1 = __ldcg(&cf[1]), h2 = __ldcg(&cf[2]);
+			cm[i].fsum[j][0] = h0.x + h0.y, cm[i].fsum[j][1] = h1.x + h1.y, cm[i].fsum[j][2] = h2.x + h2.y;
+		} else {
+			cm[i].fsum[j][0] = filled ? ff_sum(F.ff, S.U, j, id.x) : 0.0f;
+			cm[i].fsum[j][1] = filled ? ff_sum(F.ff, S.U, j, id.y) : 0.0f;
+			cm[i].fsum[j][2] = filled ? ff_sum(F.ff, S.U, j, id.z) : 0.0f;
+		}
 	}
 	__syncthreads();
 	// what travels of a record: the header and the first `rows` entries of its form-factor table
@@ -704,7 +755,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 	}
 	if (warp != 0) return;
 	if (!s_ok) {
-		if (lane == 0) *F.error = 1, *F.nsched = 0, *F.viol = 0;
+		if (lane == 0) *F.error = *F.error ? *F.error : 12, *F.nsched = 0, *F.viol = 0;	// 12: a rank's candidate records did not arrive
 		return;
 	}
 	// ---- the chain: lane l replays the shots on candidates l + 32 c
@@ -891,7 +942,7 @@ __global__ void __launch_bounds__(kApplyBlock, RADK_APPLY_MINB) apply_kernel(Dev
 					unsigned spins = 0;
 					unsigned long long w;
 					while (((w = *vp) >> 8) != want) {
-						if ((++spins & 0xfff) == 0 && clock64() - t0 > 40000000000ll) { *F.error = 1; w = 0; break; }
+						if ((++spins & 0xfff) == 0 && clock64() - t0 > 40000000000ll) { *F.error = 13; w = 0; break; }	// 13: a rank's first violation did not arrive
 					}
 					const int vt = (int)(w & 0xffull);
 					v = vt < v ? vt : v;

@@ -9,6 +9,9 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# tests/test_gpu_multi.py runs several ranks on ONE device, each rank's kernels waiting for the others' mail: every
+# stream needs its own hardware queue (default 8 per device) or a waiting kernel can sit in front of the sender
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
