@@ -485,8 +485,14 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 }
 
 // ---- batched form factors -----------------------------------------------------------------------
-constexpr int kFFBlock = 128;	// small CTAs: 128 x 2 vertices (measured 64 / 128 / 256 / 512 threads: church 3.37 / 3.19 / 3.23 / 3.51 ms)
-constexpr int kFFItems = 2;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
+#ifndef RADK_FF_BLOCK
+#define RADK_FF_BLOCK 128
+#endif
+#ifndef RADK_FF_ITEMS
+#define RADK_FF_ITEMS 2
+#endif
+constexpr int kFFBlock = RADK_FF_BLOCK;	// small CTAs: 128 x 2 vertices (measured 64 / 128 / 256 / 512 threads: church 3.37 / 3.19 / 3.23 / 3.51 ms)
+constexpr int kFFItems = RADK_FF_ITEMS;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
 				// 2: 3.59 / 1.27 / 3.61, 4: 3.61 / 1.32 / 3.69, 8: 3.92 / 1.47 / 4.07)
 
 // 48 warps per SM (40 registers): measured 32 / 40 / 48 / 64 warps per SM on church 4.06 / 3.46 / 3.20 / 3.35 ms (64 = 32
