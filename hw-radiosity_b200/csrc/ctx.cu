@@ -542,15 +542,16 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		// use the same value, which the candidate mail checks)
 		size_t free_b = 0, total_b = 0;
 		CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-		// Default: 64 candidates per round when a rank holds fewer than 200 000 receivers, else 32.  Small shards are bound
-		// by the per-round latency chain and by form-factor launches too small to fill the device; large ones by the rows
-		// speculation fills and never uses when a long schedule is cut short (measured at 32 / 48 / 64 rows, ms per run:
-		// church 116 791 receivers 3.93 / 3.83 / 3.82, box 98 734: 2.11 / 2.02 / 1.94, room 332 204 (200 shots): 3.74 / 3.95 /
-		// 4.04; church on 8 GPUs 2.07 at 32, 1.33 at 64, 1.39 at 128).  The rule only uses numbers every rank agrees on.
+		// Default candidates per round by receivers per rank: < 50 000: 64, < 200 000: 48, else 32.  Small shards are bound by
+		// the per-round latency chain and by form-factor launches too small to fill the device; with long schedules more
+		// rounds are cut short by an overtaking receiver and pay the apply pass twice.  Measured at 32 / 48 / 64 rows, ms to
+		// convergence: church (116 791 receivers) 3.92 / 3.83 / 3.81, box (98 734) 28.2 / 29.3 / 31.7, room (332 204, first 3000
+		// shots) 57.2 / 57.3 / 60.5; church on 8 GPUs (14 599 per rank) 2.07 / - / 1.33, 1.39 at 128.  The rule only uses
+		// numbers every rank agrees on.
 		const char *env_rows = getenv("RADK_FF_ROWS");
 		// -parallel_src P: an iteration needs P rows at once; four iterations per round where kMaxRows allows it
 		const int P = std::max(1, std::min(o.parallel_src, kMaxSources));
-		const int def_rows = P > 1 ? std::min(kMaxRows, std::max(32, (4 * P + 31) / 32 * 32)) : (F.leaves_total / world < 200000 ? 64 : 32);
+		const int def_rows = P > 1 ? std::min(kMaxRows, std::max(32, (4 * P + 31) / 32 * 32)) : (F.leaves_total / world < 50000 ? 64 : (F.leaves_total / world < 200000 ? 48 : 32));
 		int rows = o.ff_rows > 0 ? std::min(o.ff_rows, kMaxRows) : (env_rows && atoi(env_rows) > 0 ? std::min(atoi(env_rows), kMaxRows) : def_rows);
 		while (rows > 2 && (size_t)rows * std::max(U, 1) * sizeof(float2) > free_b / 4) rows >>= 1;
 		if (rows < P) { set_error("the form-factor cache cannot hold one row per -parallel_src shooter"); return RADK_ERR_LIMIT; }
