@@ -249,6 +249,12 @@ def extra_workload(name, rank, world, local_rank, barrier, max_over_ranks, flush
     if gold:
         out["reference_equivalent_rays"] = gold["rays"]
         out["rays_per_s"] = gold["rays"] / (min(ms[1:]) * 1e-3)
+    # bytes side of the SURVEY 8(d) bound with EVERY receiver of the frozen mesh counted as shaded in every shot (saturated
+    # receivers are not subtracted: an upper bound on the algorithmic bytes, so the fraction is an upper bound too)
+    leaves = int((model.triangles["parent"] >= 0).sum())
+    hbm_gbs = measured_peaks()[0] * world
+    out["roofline_bytes_side"] = {"receivers": leaves, "bound_us_per_shot": ALGO_BYTES_PER_RECEIVER * leaves / (hbm_gbs * 1e9) * 1e6,
+                                  "frac_upper_bound": ALGO_BYTES_PER_RECEIVER * leaves * max(done, 1) / (hbm_gbs * 1e9) / (min(ms[1:]) * 1e-3)}
     ctx.close()
     model.close()
     barrier()
