@@ -834,8 +834,18 @@ int radk_ctx_profile(radk_ctx *c, long long max_shots, double ms[3], long long n
 	const long long before = *c->h_shots;
 	for (int k = 0; k < 3; k++) ms[k] = 0, n[k] = 0;
 	constexpr int kProfRounds = 8;
-	cudaEvent_t ev[4 * kProfRounds];
-	for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+	struct Events {		// destroyed on every exit, also the error returns below
+		cudaEvent_t e[4 * kProfRounds] = {};
+		radk_ctx *c;
+		bool ok = false;
+		explicit Events(radk_ctx *ctx) : c(ctx) {}
+		~Events() {
+			for (auto &x : e) if (x) cudaEventDestroy(x);
+			if (!ok) c->have_current = false;	// a partial iteration leaves rec[cur] behind the device state
+		}
+	} evh(c);
+	cudaEvent_t *ev = evh.e;
+	for (int i = 0; i < 4 * kProfRounds; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
 	const bool stats = c->opt.collect_stats != 0;
 	long long done = 0;
 	if (c->use_fast) {
@@ -888,7 +898,7 @@ int radk_ctx_profile(radk_ctx *c, long long max_shots, double ms[3], long long n
 			if (c->h_flags->converged) break;
 		}
 	}
-	for (auto &e : ev) cudaEventDestroy(e);
+	evh.ok = true;
 	if (shots) *shots = done;
 	CUDA_TRY(cudaGetLastError());
 	return RADK_OK;

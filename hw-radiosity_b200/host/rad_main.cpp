@@ -269,16 +269,23 @@ int main(int argc, char **argv) {
 		}
 	radk_ctx *ctx = ctxs[0];
 	// all ranks step together (each blocks on its own stream while exchanging candidates with its peers)
+	std::vector<std::string> step_err((size_t)ngpu);
+	int failed_rank = -1;
 	auto step_all = [&](long long chunk, long long *done, int *converged) {
 		if (ngpu == 1) return radk_ctx_step(ctx, chunk, done, converged);
 		std::vector<int> rc((size_t)ngpu, RADK_OK);
 		std::vector<long long> d((size_t)ngpu, 0);
 		std::vector<int> cv((size_t)ngpu, 0);
 		std::vector<std::thread> th;
-		for (int r = 0; r < ngpu; r++) th.emplace_back([&, r] { rc[r] = radk_ctx_step(ctxs[r], chunk, &d[r], &cv[r]); });
+		// radk_last_error() is per thread: each worker keeps its own message
+		for (int r = 0; r < ngpu; r++)
+			th.emplace_back([&, r] {
+				rc[r] = radk_ctx_step(ctxs[r], chunk, &d[r], &cv[r]);
+				if (rc[r] != RADK_OK) step_err[r] = radk_last_error();
+			});
 		for (auto &t : th) t.join();
 		for (int r = 0; r < ngpu; r++)
-			if (rc[r] != RADK_OK) return rc[r];
+			if (rc[r] != RADK_OK) { failed_rank = r; return rc[r]; }
 		*done = d[0], *converged = cv[0];
 		return (int)RADK_OK;
 	};
@@ -292,7 +299,8 @@ int main(int argc, char **argv) {
 		long long done = 0;
 		int converged = 0;
 		if (step_all(chunk, &done, &converged) != RADK_OK) {
-			fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
+			if (failed_rank >= 0) fprintf(stderr, "[" KRED "ERR" KWHT "] rank %d: %s\n", failed_rank, step_err[failed_rank].c_str());
+			else fprintf(stderr, "[" KRED "ERR" KWHT "] %s\n", radk_last_error());
 			return 1;
 		}
 		shots += done;
@@ -302,7 +310,7 @@ int main(int argc, char **argv) {
 		}
 		if (shots % W == 0) {
 			fprintf(stderr, "[" KGRN "INFO" KWHT "] Loop %lld BEGIN\n", shots);
-			write_snapshot(ctxs, model, o, (int)shots);
+			if (!write_snapshot(ctxs, model, o, (int)shots)) return 1;
 			fprintf(stderr, "[" KGRN "INFO" KWHT "] END Loop. There are %i triangles.\n", radk_ctx_trinum(ctx));
 		}
 	}

@@ -86,3 +86,26 @@ def state_digest(tri):
     live = tri["parent"] >= 0
     return {"trinum": len(tri), "leaves": int(live.sum()), "accB_sha": sha(tri["accB"][live]),
             "deltaB_sha": sha(tri["deltaB"][live])}
+
+
+def nan_prone_rays(tri, n0, n, seed=5):
+    """Rays that stress the NaN rule of leaf_visit (rt_core.cuh): from receiver vertices toward vertices, edge midpoints and
+    centres of leaves that are slot neighbours (siblings, children of the neighbouring original) or random - many run
+    along an edge or inside the plane of an occluder through their origin (a1 == a2 == 0, t = 0/0).  Each ray asks for
+    its own target's original.  Returns p, v, banned original (or -1), logsrc."""
+    rng = np.random.default_rng(seed)
+    leaves = np.nonzero(tri["parent"] >= 0)[0]
+    a = rng.choice(leaves, n)
+    near = np.clip(a + rng.integers(-40, 41, n), 0, len(tri) - 1)
+    near = np.where(tri["parent"][near] >= 0, near, a)
+    b = np.where(rng.random(n) < 0.7, near, rng.choice(leaves, n))
+    p = tri["p"][a, rng.integers(0, 3, n)].copy()
+    kind = rng.integers(0, 3, n)
+    vsel = tri["p"][b, rng.integers(0, 3, n)]
+    mid = ((tri["p"][b, 0] + tri["p"][b, 1]) / 2).astype(np.float32)
+    tgt = np.where(kind[:, None] == 0, tri["c"][b], np.where(kind[:, None] == 1, vsel, mid)).astype(np.float32)
+    logsrc = tri["parent"][b].astype(np.int32).copy()
+    frm = np.where(rng.random(n) < 0.5, tri["parent"][a], -1).astype(np.int32)
+    v = (tgt - p).astype(np.float32)
+    keep = np.abs(v).sum(axis=1) > 0
+    return tuple(np.ascontiguousarray(x[keep]) for x in (p, v, frm, logsrc))

@@ -333,6 +333,26 @@ def test_ray_sees_matches_oracle(hr, po, models_dir):
         assert visible > 0                                               # the sample does contain visible rays
 
 
+def test_nan_prone_rays_match_oracle_on_device(hr, po, models_dir):
+    """The NaN rule of leaf_visit on the device (radk_ray_sees): rays along edges / inside occluder planes, each toward
+    its own original, grouped by original for the probe."""
+    from conftest import nan_prone_rays
+    for name in ["church", "box"]:
+        m = hr.Model(str(models_dir / f"{name}.tri"))
+        sc = oracle_scene(po, m)
+        ctx = hr.Context(m)
+        p, v, frm, logsrc = nan_prone_rays(m.triangles, m.n0, 40000, seed=9)
+        want = sc.ray_hitted(p, v, frm)
+        ids, counts = np.unique(logsrc, return_counts=True)
+        checked = mismatches = 0
+        for src in ids[np.argsort(-counts)][:120]:      # the originals with the most rays
+            sel = logsrc == src
+            got = ctx.ray_sees(p[sel], v[sel], frm[sel], int(src))
+            mismatches += int((got.astype(bool) != (want[sel] == src)).sum())
+            checked += int(sel.sum())
+        assert mismatches == 0 and checked > 1000, (name, mismatches, checked)
+
+
 def test_select_matches_oracle(hr, po, models_dir):
     m = hr.Model(str(models_dir / "church.tri"))
     sc = oracle_scene(po, m, parallel_src=6)

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, oracle_scene
+from conftest import ROOT, nan_prone_rays, oracle_scene
 
 
 @pytest.fixture(scope="module")
@@ -183,3 +183,17 @@ def test_chained_loop_with_parallel_sources_matches_oracle(hr, po, emu, models_d
     assert list(sh[: ns.value]) == [s[0] for s in seq]
     assert np.array_equal(accB[live].view(np.uint32), sc.slots["accB"][live].view(np.uint32))
     assert np.array_equal(dB[live].view(np.uint32), sc.slots["deltaB"][live].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["church", "room", "box"])
+def test_nan_prone_rays_match_oracle(hr, po, emu, models_dir, name):
+    """leaf_visit's NaN rule (an entry with t = 0/0 ends the walk in its leaf; logsrc survives it only with a larger
+    index) against the oracle's sequential TriListHitted on rays built to run along edges and inside occluder planes."""
+    m = hr.Model(str(models_dir / f"{name}.tri"))
+    sc = oracle_scene(po, m)
+    p, v, frm, logsrc = nan_prone_rays(m.triangles, m.n0, 60000)
+    want = sc.ray_hitted(p, v, frm)
+    got = np.empty(len(p), np.int32)
+    assert emu.emu_sees(C.addressof(m.scene), p.ctypes.data, v.ctypes.data, frm.ctypes.data, logsrc.ctypes.data, len(p), got.ctypes.data) == 0
+    assert np.array_equal(got.astype(bool), want == logsrc)
+    assert (want == logsrc).sum() > 1000 and (want != logsrc).sum() > 1000
