@@ -29,6 +29,47 @@
 
 namespace radk {
 
+// ---- TMA 1-D bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier) -------------------------
+// A CTA's read-only tile (the shooter record and the 4 KB of vertices it works on; the round's schedule in the
+// apply pass) is fetched by ONE thread as a bulk asynchronous copy instead of one load per thread; everybody
+// waits on the mbarrier's phase.  Addresses and sizes are multiples of 16 bytes.
+// Measured (church / box / room, ms per run, same box): the schedule copy of the apply pass is neutral to slightly
+// faster (update 0.544 -> 0.538) and is ON; staging ff_batch_kernel's tile costs 2 % (church 3.86 -> 3.94: a CTA lives
+// for ~128 rays, the copy's latency sits in front of every one of its 26 000 CTAs per launch while the plain loads it
+// replaces were coalesced and hit L1 on re-use) and is OFF (RADK_TMA_FF=1 builds it).
+#ifndef RADK_TMA_APPLY
+#define RADK_TMA_APPLY 1
+#endif
+#ifndef RADK_TMA_FF
+#define RADK_TMA_FF 0
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned arrivals) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");	// visible to the async proxy before the copies are issued
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+		     "r"(bytes), "r"(smem_u32(bar))
+		     : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+
 constexpr int kPredictGroups = 2048;	// groups for the approximate top-K (= 2 keys per thread of the last CTA)
 
 struct ShotRec {		// the shooter of the next shot as the prediction sees it (diagnostics)
@@ -501,16 +542,33 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 	const int j = blockIdx.z;
 	if (j >= *F.ntodo) return;
 	const int row = F.todo[j], half = blockIdx.y;
-	__shared__ ShooterRec sh;
+	__shared__ __align__(16) ShooterRec sh;
 	__shared__ int q_u[kFFBlock * kFFItems];
 	__shared__ int wcount[kFFItems * (kFFBlock / 32)];
 	__shared__ int s_next;
+	const int base = blockIdx.x * (kFFBlock * kFFItems);
+#if RADK_TMA_FF
+	// the CTA's tile - its shooter record and its vertices - by two bulk copies of one thread
+	static_assert(sizeof(ShooterRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
+	__shared__ __align__(16) float4 s_uv[kFFBlock * kFFItems];
+	__shared__ __align__(8) unsigned long long s_bar;
+	if (threadIdx.x == 0) {
+		s_next = 0;
+		mbar_init(&s_bar, 1);
+		const int nv = min(kFFBlock * kFFItems, S.U - base);
+		mbar_expect_tx(&s_bar, (unsigned)(sizeof(ShooterRec) + nv * sizeof(float4)));
+		tma_load_1d(&sh, F.rec + row, (unsigned)sizeof(ShooterRec), &s_bar);
+		tma_load_1d(s_uv, S.uv + base, (unsigned)(nv * sizeof(float4)), &s_bar);
+	}
+	__syncthreads();	// the barrier is initialised before anybody polls it
+	mbar_wait(&s_bar, 0u);
+#else
 	if (threadIdx.x < sizeof(ShooterRec) / 4) ((int *)&sh)[threadIdx.x] = ((const int *)(F.rec + row))[threadIdx.x];
-	const unsigned *row_mask = F.row_mask + (size_t)row * F.mask_words;	// bit n: leaf n lists the shooter's original (read through L1)
 	if (threadIdx.x == 0) s_next = 0;
 	__syncthreads();
+#endif
+	const unsigned *row_mask = F.row_mask + (size_t)row * F.mask_words;	// bit n: leaf n lists the shooter's original (read through L1)
 	float2 *out = F.ff + (size_t)row * S.U;
-	const int base = blockIdx.x * (kFFBlock * kFFItems);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	if (!sh.splittable && half == 1) {	// the single centre sample is handled by half 0
 		for (int it = 0; it < kFFItems; it++) {
@@ -530,7 +588,11 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 		const int u = base + it * kFFBlock + threadIdx.x;
 		live[it] = false;
 		if (u < S.U) {
+#if RADK_TMA_FF
+			const float4 v = s_uv[it * kFFBlock + threadIdx.x];
+#else
 			const float4 v = __ldg(&S.uv[u]);
+#endif
 			const float4 pn = __ldg(&S.par_n[__float_as_int(v.w)]);
 			float dx, dy, dz;
 			const float ff = ff_geom(*smp, pn.x, pn.y, pn.z, pn.w, v.x, v.y, v.z, dx, dy, dz, live[it]);
@@ -572,7 +634,11 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 				more = false;
 			} else {
 				u = q_u[i];
+#if RADK_TMA_FF
+				const float4 v = s_uv[u - base];
+#else
 				const float4 v = __ldg(&S.uv[u]);
+#endif
 				px = v.x, py = v.y, pz = v.z, ban = __float_as_int(v.w);
 				vx = smp->cx - px, vy = smp->cy - py, vz = smp->cz - pz;
 				prev = -1, sg = 0, t = 0.f;
@@ -927,7 +993,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 constexpr int kApplyBlock = RADK_APPLY_BLOCK;
 template <bool COMMIT, bool MULTI>	// MULTI: -parallel_src > 1 (iterations with co-shooters)
 __global__ void __launch_bounds__(kApplyBlock, RADK_APPLY_MINB) apply_kernel(DevScene S, FastState F) {
-	__shared__ ShotSched sched[kMaxChain];
+	__shared__ __align__(32) ShotSched sched[kMaxChain];
 	__shared__ int s_n, s_wmin[kApplyBlock / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int K = *F.nsched;
@@ -990,8 +1056,21 @@ __global__ void __launch_bounds__(kApplyBlock, RADK_APPLY_MINB) apply_kernel(Dev
 		if (n >= K) return;	// the whole schedule was valid: the apply pass already wrote the right state
 	}
 	if (n <= 0) return;
+#if RADK_TMA_APPLY
+	{	// the round's schedule (n x 32 bytes) by one bulk copy
+		__shared__ __align__(8) unsigned long long s_bar;
+		if (threadIdx.x == 0) {
+			mbar_init(&s_bar, 1);
+			mbar_expect_tx(&s_bar, (unsigned)(n * sizeof(ShotSched)));
+			tma_load_1d(sched, F.sched, (unsigned)(n * sizeof(ShotSched)), &s_bar);
+		}
+		__syncthreads();
+		mbar_wait(&s_bar, 0u);
+	}
+#else
 	for (int k = threadIdx.x; k < n; k += kApplyBlock) sched[k] = F.sched[k];
 	__syncthreads();
+#endif
 	const int r = blockIdx.x * kApplyBlock + threadIdx.x;
 	int viol = n;
 	if (r < S.R) {
