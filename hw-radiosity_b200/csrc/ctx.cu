@@ -240,7 +240,11 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 	// the side stream exists only where it is used: every stream takes one of the device's few hardware queues, and
 	// ranks that share a device (tests) deadlock when a kernel waiting for a peer's mail is queued in front of the
 	// peer's kernel that sends it
-	if (c->overlap && !c->side) CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+	if (c->overlap && !c->side) {
+		int lo = 0, hi = 0;
+		CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));	// greatest priority: the side branch's few CTAs go first
+		CUDA_TRY(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+	}
 	cudaStream_t sd = c->overlap ? c->side : st;
 	if (c->overlap) {
 		CUDA_TRY(cudaEventRecord(c->ev_fork, st));
@@ -318,6 +322,16 @@ bool build_loop_graph(radk_ctx *c) {
 		if (k.dep0 >= 0) deps[nd++] = nodes[k.dep0];
 		if (k.dep1 >= 0) deps[nd++] = nodes[k.dep1];
 		if (cudaGraphAddKernelNode(&nodes[i], body, nd ? deps : nullptr, nd, &kp) != cudaSuccess) { ok = false; break; }
+		if ((int)i == kcand || (int)i == kchain) {
+			// the side branch goes first: its CTAs are taken ahead of the thousands ff_batch_kernel still has pending
+			// (without the priority it only ran when ff_batch_kernel's last wave had been handed out)
+			int lo = 0, hi = 0;
+			cudaDeviceGetStreamPriorityRange(&lo, &hi);	// hi = numerically lowest = greatest priority
+			cudaKernelNodeAttrValue v;
+			memset(&v, 0, sizeof(v));
+			v.priority = hi;
+			if (cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributePriority, &v) != cudaSuccess) cudaGetLastError();
+		}
 	}
 	cudaGraphExec_t exec = nullptr;
 	if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) ok = false;

@@ -529,8 +529,14 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 #ifndef RADK_FF_BLOCK
 #define RADK_FF_BLOCK 128
 #endif
+// Threshold refill (round 2): idle lanes fetch new rays only when fewer than 16 lanes of the warp still walk, 4 candidate
+// vertices per thread.  Measured against per-lane refill with 2 per thread (ms per run, same box): church 3.85 -> 3.78,
+// box 2.07 -> 2.01, room 3.76 -> 3.67; threshold 8: 3.80 / 2.00 / 3.65, 24: 3.84 / 2.05 / 3.81; 8 per thread: 4.11 / 2.17 / 3.95.
+#ifndef RADK_FF_REFILL_T
+#define RADK_FF_REFILL_T 16
+#endif
 #ifndef RADK_FF_ITEMS
-#define RADK_FF_ITEMS 2
+#define RADK_FF_ITEMS 4
 #endif
 constexpr int kFFBlock = RADK_FF_BLOCK;	// small CTAs: 128 x 2 vertices (measured 64 / 128 / 256 / 512 threads: church 3.37 / 3.19 / 3.23 / 3.51 ms)
 constexpr int kFFItems = RADK_FF_ITEMS;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
@@ -628,7 +634,14 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 	float px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, t = 0;
 	bool more = true;
 	for (;;) {
+#if RADK_FF_REFILL_T < 32
+		// idle lanes fetch new rays only when fewer than RADK_FF_REFILL_T lanes of the warp still walk: the fetched rays
+		// start their walks together instead of each lane drifting into its own phase
+		const bool refill = __popc(__ballot_sync(0xffffffffu, u >= 0)) < RADK_FF_REFILL_T;
+		if (u < 0 && more && refill) {
+#else
 		if (u < 0 && more) {
+#endif
 			const int i = atomicAdd(&s_next, 1);
 			if (i >= total) {
 				more = false;
