@@ -15,7 +15,7 @@ from conftest import GOLDEN_DIR, ROOT
 ROWS = 8      # cache rows = candidates per round (small, so that rounds end on violations too)
 
 
-def _worker(rank, world, port, model_gz, shots, out_dir):
+def _worker(rank, world, port, model_gz, shots, out_dir, psrc=1):
     import gzip
     import tempfile
 
@@ -30,7 +30,10 @@ def _worker(rank, world, port, model_gz, shots, out_dir):
     emu.emu_shard_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
     for f in ("emu_shard_top", "emu_shard_begin", "emu_shard_cands"):
         getattr(emu, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    emu.emu_shard_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    emu.emu_shard_chain2.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]
+    emu.emu_shard_set_parallel_src.argtypes = [C.c_void_p, C.c_int]
+    emu.emu_shard_count.restype = C.c_longlong
+    emu.emu_shard_count.argtypes = [C.c_void_p]
     emu.emu_shard_apply.argtypes = [C.c_void_p]
     emu.emu_shard_commit.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     emu.emu_shard_state.argtypes = [C.c_void_p] * 4
@@ -42,6 +45,7 @@ def _worker(rank, world, port, model_gz, shots, out_dir):
             f.write(gzip.open(model_gz).read())
         m = hr.Model(tri)
     h = emu.emu_shard_open(C.addressof(m.scene), rank, world, rows, 1200.0)
+    emu.emu_shard_set_parallel_src(h, psrc)          # -parallel_src: co-shooters per iteration
 
     def all_gather(arr):
         mine = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy())
@@ -55,6 +59,8 @@ def _worker(rank, world, port, model_gz, shots, out_dir):
         keys, recs = np.zeros(rows, np.uint64), np.zeros(rows * nrec, np.uint8)
         emu.emu_shard_top(h, keys.ctypes.data, recs.ctypes.data)
         gk = np.concatenate([p.view(np.uint64) for p in all_gather(keys)])
+        # ... and with -parallel_src every rank's part of |C| (the one extra all-reduced count of SURVEY.md 8e)
+        count = sum(int(p.view(np.int64)[0]) for p in all_gather(np.array([emu.emu_shard_count(h)], np.int64)))
         gr = np.concatenate(all_gather(recs)).reshape(world * rows, nrec)
         order = np.argsort(gk, kind="stable")[::-1][:rows]
         top, toprec = np.ascontiguousarray(gk[order]), np.ascontiguousarray(gr[order])
@@ -70,7 +76,7 @@ def _worker(rank, world, port, model_gz, shots, out_dir):
             o = go[r].view(np.int32).astype(bool)
             merged[o] = gc[r].reshape(rows, ncand)[o]
         merged = np.ascontiguousarray(merged)
-        emu.emu_shard_chain(h, merged.ctypes.data, shots - len(log))
+        emu.emu_shard_chain2(h, merged.ctypes.data, shots - len(log), count)
         # exchange 3: the first violation of the schedule
         viol = np.array([emu.emu_shard_apply(h)], np.int32)
         v = min(int(p.view(np.int32)[0]) for p in all_gather(viol))
@@ -90,24 +96,24 @@ def _worker(rank, world, port, model_gz, shots, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world,shots", [("sbox", 2, 45), ("model3s", 3, 60)])
-def test_two_rank_gloo_exchange_matches_oracle(hr, po, models_dir, tmp_path, name, world, shots):
+@pytest.mark.parametrize("name,world,shots,psrc", [("sbox", 2, 45, 1), ("model3s", 3, 60, 1), ("sbox", 2, 30, 3)])
+def test_two_rank_gloo_exchange_matches_oracle(hr, po, models_dir, tmp_path, name, world, shots, psrc):
     from conftest import oracle_scene
     test_hostemu = __import__("test_hostemu")      # builds libhostemu.so if stale
     so = os.path.join(ROOT, "tests", "hostemu", "libhostemu.so")
     if not os.path.exists(so):
         pytest.skip("hostemu not built")
     port = 29500 + (os.getpid() % 400)
-    mp.spawn(_worker, args=(world, port, os.path.join(GOLDEN_DIR, "models", f"{name}.tri.gz"), shots, str(tmp_path)),
+    mp.spawn(_worker, args=(world, port, os.path.join(GOLDEN_DIR, "models", f"{name}.tri.gz"), shots, str(tmp_path), psrc),
              nprocs=world, join=True)
     m = hr.Model(str(models_dir / f"{name}.tri"))
-    sc = oracle_scene(po, m)
+    sc = oracle_scene(po, m, parallel_src=psrc)
     seq = sc.run(shots)
     seen = 0
     for r in range(world):
         d = np.load(tmp_path / f"rank{r}.npz")
         assert list(d["log"]) == [s[0] for s in seq]
-        assert int(d["rounds"]) < shots            # shots really were batched
+        assert int(d["rounds"]) < shots or psrc > 1  # shots really were batched (co-shooters: |C| is small here, one iteration per round)
         slots = d["slots"]
         seen += len(slots)
         assert np.array_equal(d["acc"].reshape(-1, 3, 3).view(np.uint32), sc.slots["accB"][slots].view(np.uint32))
