@@ -224,6 +224,22 @@ int reset_fast_state(radk_ctx *c) {
 	return RADK_OK;
 }
 
+// CUDA loads a kernel's code at its first launch (lazy module loading), and that load can wait for kernels already
+// running on the device.  Kernels of this path WAIT for their peers' mail: with several ranks on one device (tests,
+// `rad -gpus N` on fewer devices) a rank's first launch of, say, predict_exact_kernel would sit behind the other rank's
+// spinning merge kernel until the device-side timeout.  So every kernel of the round is loaded when a context is created.
+int preload_round_kernels() {
+	const void *fns[] = {(const void *)predict_kernel, (const void *)predict_exact_kernel, (const void *)predict_merge_kernel,
+			     (const void *)ff_batch_kernel<1>, (const void *)ff_batch_kernel<2>, (const void *)ff_batch_kernel<4>,
+			     (const void *)chain_kernel, (const void *)apply_kernel<false, false>, (const void *)apply_kernel<true, false>,
+			     (const void *)apply_kernel<false, true>, (const void *)apply_kernel<true, true>};
+	for (const void *f : fns) {
+		cudaFuncAttributes a;
+		CUDA_TRY(cudaFuncGetAttributes(&a, f));
+	}
+	return RADK_OK;
+}
+
 // One round of the fast path: predict -> batched form factors -> chain -> apply -> commit.
 // ev (optional): 4 events recorded around the three kernel classes, for profiling.
 int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
@@ -250,11 +266,14 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 		CUDA_TRY(cudaEventRecord(c->ev_fork, st));
 		CUDA_TRY(cudaStreamWaitEvent(sd, c->ev_fork, 0));
 	}
-	ff_cand_kernel<<<dim3((unsigned)((c->rows * 6 + 127) / 128), (unsigned)c->rows), 128, 0, sd>>>(c->S, F);
-	chain_kernel<<<1, 256, chain_smem_bytes(c->rows), sd>>>(c->S, F);
+	chain_kernel<<<kChainGrid, kChainBlock, chain_smem_bytes(c->rows), sd>>>(c->S, F);
 	if (c->overlap) CUDA_TRY(cudaEventRecord(c->ev_join, sd));
-	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows);
-	ff_batch_kernel<<<g, kFFBlock, 0, st>>>(c->S, F);
+	const int items = ff_items_for(c->U, c->rows);
+	const dim3 g((unsigned)std::max(1, (c->U + kFFBlock * items - 1) / (kFFBlock * items)), 2, (unsigned)c->rows);
+	{
+		void *args[] = {(void *)&c->S, (void *)&F};
+		CUDA_TRY(cudaLaunchKernel(ff_batch_fn(items), g, dim3(kFFBlock), args, 0, st));
+	}
 	if (c->overlap) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	const int nb = std::max(1, (c->R + kApplyBlock - 1) / kApplyBlock);
@@ -266,7 +285,7 @@ int launch_fast_round(radk_ctx *c, cudaEvent_t *ev) {
 		apply_kernel<true, false><<<nb, kApplyBlock, 0, st>>>(c->S, F);
 	}
 	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-	c->launches += 6;
+	c->launches += 5;
 	return RADK_OK;
 }
 
@@ -299,10 +318,11 @@ bool build_loop_graph(radk_ctx *c) {
 	int last = add((const void *)predict_kernel, dim3(64), dim3(1024), 0, -1);
 	if (c->F.parallel_src > 1) last = add((const void *)predict_exact_kernel, dim3(64), dim3(1024), 0, last);
 	if (c->F.world > 1) last = add((const void *)predict_merge_kernel, dim3(1), dim3(1024), 0, last);
-	// fork: the form factors of all vertices | the candidates' own form factors, then the chain (a single warp)
-	const int kcand = add((const void *)ff_cand_kernel, dim3((unsigned)((c->rows * 6 + 127) / 128), (unsigned)c->rows), dim3(128), 0, last);
-	const int kff = add((const void *)ff_batch_kernel, dim3((unsigned)std::max(1, (c->U + kFFBlock * kFFItems - 1) / (kFFBlock * kFFItems)), 2, (unsigned)c->rows), dim3(kFFBlock), 0, last);
-	const int kchain = add((const void *)chain_kernel, dim3(1), dim3(256), chain_smem_bytes(c->rows), kcand);
+	// fork: the form factors of all vertices | the candidates' own form factors + the chain (chain_kernel, added first:
+	// its few CTAs must be resident before ff_batch_kernel fills the device)
+	const int kchain = add((const void *)chain_kernel, dim3(kChainGrid), dim3(kChainBlock), chain_smem_bytes(c->rows), last);
+	const int items = ff_items_for(c->U, c->rows);
+	const int kff = add(ff_batch_fn(items), dim3((unsigned)std::max(1, (c->U + kFFBlock * items - 1) / (kFFBlock * items)), 2, (unsigned)c->rows), dim3(kFFBlock), 0, last);
 	if (c->F.parallel_src > 1) {
 		last = add((const void *)apply_kernel<false, true>, dim3(nb), dim3(kApplyBlock), 0, kff, kchain);
 		last = add((const void *)apply_kernel<true, true>, dim3(nb), dim3(kApplyBlock), 0, last);
@@ -322,7 +342,7 @@ bool build_loop_graph(radk_ctx *c) {
 		if (k.dep0 >= 0) deps[nd++] = nodes[k.dep0];
 		if (k.dep1 >= 0) deps[nd++] = nodes[k.dep1];
 		if (cudaGraphAddKernelNode(&nodes[i], body, nd ? deps : nullptr, nd, &kp) != cudaSuccess) { ok = false; break; }
-		if ((int)i == kcand || (int)i == kchain) {
+		if ((int)i == kchain) {
 			// the side branch goes first: its CTAs are taken ahead of the thousands ff_batch_kernel still has pending
 			// (without the priority it only ran when ff_batch_kernel's last wave had been handed out)
 			int lo = 0, hi = 0;
@@ -571,6 +591,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		if (rows < P) { set_error("the form-factor cache cannot hold one row per -parallel_src shooter"); return RADK_ERR_LIMIT; }
 		c->rows = rows;
 		CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes(kMaxRows)));
+		{ const int prc = preload_round_kernels(); if (prc) return prc; }
 		CUDA_TRY(c->ffcache.alloc((size_t)rows * std::max(U, 1)));
 		CUDA_TRY(c->row_slot.alloc(kMaxRows));
 		CUDA_TRY(c->slot_row.alloc(std::max(s->trinum, 1)));
@@ -597,7 +618,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.ff = c->ffcache.p, F.rows = rows, F.row_slot = c->row_slot.p, F.slot_row = c->slot_row.p;
 		F.rec = c->row_rec.p, F.todo = c->todo.p, F.ntodo = c->fast_ints.p;
 		F.nsched = c->fast_ints.p + 1, F.viol = c->fast_ints.p + 2;
-		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.apply_ticket = c->fast_uints.p + 1;
+		F.group_key = c->group_key.p, F.ticket = c->fast_uints.p, F.apply_ticket = c->fast_uints.p + 1, F.chain_ticket = c->fast_uints.p + 3;
 		F.handoff = c->handoff.p, F.budget = c->budget.p;
 		F.sched = c->sched.p, F.counters = c->counters.p;
 		for (int v = 0; v < 3; v++) F.st_prev[v] = c->st_prev[v].p;
@@ -609,7 +630,7 @@ int upload_scene(radk_ctx *c, const radk_scene *s) {
 		F.parallel_src = P, F.local_count = c->fast_uints.p + 2, F.cand_count = c->cand_count.p, F.exact = c->exact.p;
 		F.cand_ff = c->cand_ff.p;
 		F.dbg = nullptr;
-		if (getenv("RADK_DEBUG_PREDICT")) { CUDA_TRY(c->dbg.alloc(16)); CUDA_TRY(cudaMemsetAsync(c->dbg.p, 0, 16 * 8, st)); F.dbg = c->dbg.p; }
+		if (getenv("RADK_DEBUG_PREDICT")) { CUDA_TRY(c->dbg.alloc(16 + 64 * 16)); CUDA_TRY(cudaMemsetAsync(c->dbg.p, 0, (16 + 64 * 16) * 8, st)); F.dbg = c->dbg.p; }
 		c->peers_connected = world == 1;
 		int rc2 = reset_fast_state(c);
 		if (rc2) return rc2;
@@ -753,10 +774,28 @@ void radk_ctx_destroy(radk_ctx *c) {
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->dbg.p) {	// RADK_DEBUG_PREDICT: phases of the last predict_kernel launch
-		unsigned long long t[16];
-		if (cudaMemcpy(t, c->dbg.p, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
+		unsigned long long t[16 + 64 * 16];
+		if (cudaMemcpy(t, c->dbg.p, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
 			fprintf(stderr, "[radk] predict phases (ns): scan+ticket %llu, top-K %llu, cache rebuild %llu, shooter records %llu, leaf masks %llu\n",
 				t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
+			// timeline of the last (up to 64) rounds, relative to the round's predict start; then the gap to the next round
+			static const char *ev[11] = {"predict", "predict_end", "merge", "merge_end", "ff_cand", "ff_batch", "chain", "chain_end", "apply", "commit", "commit_end"};
+			const unsigned long long rounds = t[15];
+			double sum[11] = {0}, gap = 0;
+			int cnt[11] = {0}, ngap = 0;
+			const int nr = (int)std::min<unsigned long long>(rounds, 64);
+			for (int r = 0; r < nr; r++) {
+				const unsigned long long *q = t + 16 + 16 * r;
+				for (int k = 0; k < 11; k++)
+					if (q[k] >= q[0] && q[k] - q[0] < 100000000ull && q[0]) sum[k] += (double)(q[k] - q[0]), cnt[k]++;
+				const unsigned long long *nx = t + 16 + 16 * ((r + 1) % 64);
+				if (r + 1 < nr && nx[0] > q[10] && nx[0] - q[10] < 1000000ull) gap += (double)(nx[0] - q[10]), ngap++;
+			}
+			fprintf(stderr, "[radk] round timeline, mean us after the round's predict start (rank %d, %d rounds):", c->opt.rank, nr);
+			for (int k = 0; k < 11; k++)
+				if (cnt[k]) fprintf(stderr, " %s %.1f", ev[k], sum[k] / cnt[k] / 1e3);
+			fprintf(stderr, " | gap to next round %.1f\n", ngap ? gap / ngap / 1e3 : 0.0);
+		}
 	}
 	if (c->h_flags) cudaFreeHost(c->h_flags);
 	if (c->h_shots) cudaFreeHost(c->h_shots);

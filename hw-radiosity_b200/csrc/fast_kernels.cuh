@@ -128,6 +128,7 @@ struct FastState {
 	int *nsched;			// its length
 	int *viol;			// first violation found by this rank's receivers (nsched: none)
 	unsigned *apply_ticket;		// last-CTA-done counter of apply_kernel (multi-GPU: the last CTA mails viol)
+	unsigned *chain_ticket;		// last-CTA-done counter of chain_kernel's candidate-ray phase
 	float4 *st_prev[3];		// [R] the receivers' state before the round's apply pass
 	unsigned long long *counters;	// [8] 0: rows filled, 1: rounds, 2: shots scheduled, 3: shots committed, 4: rounds that re-applied
 	float2 *cand_ff;		// [kMaxRows new rows][kMaxRows candidates][3 vertices] form factors of this round's NEW rows at the
@@ -249,6 +250,16 @@ __device__ void build_row_masks(const DevScene &S, const FastState &F, int nt) {
 }
 
 // ---- predict ------------------------------------------------------------------------------------
+// RADK_DEBUG_PREDICT timeline: dbg[16 + 16 * (round % 64) + k] = %globaltimer when event k of the round happened
+// (0 predict starts, 1 predict's last CTA ends, 2 merge starts, 3 merge ends, 4 ff_cand starts, 5 ff_batch starts,
+// 6 chain starts, 7 chain ends, 8 apply starts, 9 commit starts, 10 commit's block 0 ends); dbg[15] counts rounds.
+__device__ __forceinline__ void dbg_trace(const FastState &F, int k) {
+	if (F.dbg) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		F.dbg[16 + 16 * (int)(F.dbg[15] & 63ull) + k] = t;
+	}
+}
 __device__ __forceinline__ void dbg_stamp(const FastState &F, int i) {
 	if (F.dbg && threadIdx.x == 0) {
 		unsigned long long t;
@@ -341,6 +352,7 @@ __device__ void predict_finish(const DevScene &S, const FastState &F, const unsi
 __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) {
 	__shared__ bool s_last;
 	if (blockIdx.x == 0) dbg_stamp(F, 0);
+	if (blockIdx.x == 0 && threadIdx.x == 0) dbg_trace(F, 0);
 	const int T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	// thread t only sees receivers r == t (mod T); T is a multiple of kPredictGroups, so its running
 	// maximum belongs to group t % kPredictGroups
@@ -385,6 +397,7 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		return;
 	}
 	predict_finish(S, F, keys, cs);
+	if (threadIdx.x == 0) dbg_trace(F, 1);
 }
 
 // -parallel_src P > 1, second pass of the selection: every key >= T (the P-th largest group maximum; T = 0: every
@@ -455,7 +468,7 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 	const unsigned long long round = *F.pred_round;
 	const int par = (int)(round & 1ull);
 	PeerBox *mine = F.box[F.rank];
-	if (threadIdx.x == 0) s_ok = 1;
+	if (threadIdx.x == 0) s_ok = 1, dbg_trace(F, 2);
 	__syncthreads();
 	if (threadIdx.x < F.world) {
 		if (!peer_wait(&mine->pred_seq[par][threadIdx.x], round)) s_ok = 0;
@@ -523,6 +536,7 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 	if (threadIdx.x < nt) F.rec[F.todo[threadIdx.x]].recv = S.slot_to_recv[F.rec[F.todo[threadIdx.x]].slot];
 	__syncthreads();
 	build_row_masks(S, F, nt);
+	if (threadIdx.x == 0) dbg_trace(F, 3);
 }
 
 // ---- batched form factors -----------------------------------------------------------------------
@@ -539,13 +553,18 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 #define RADK_FF_ITEMS 4
 #endif
 constexpr int kFFBlock = RADK_FF_BLOCK;	// small CTAs: 128 x 2 vertices (measured 64 / 128 / 256 / 512 threads: church 3.37 / 3.19 / 3.23 / 3.51 ms)
-constexpr int kFFItems = RADK_FF_ITEMS;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
+constexpr int kFFItemsMax = RADK_FF_ITEMS;	// candidate vertices per thread before compaction (measured on church / box / room: 1: 3.94 / 1.38 / 3.72 ms,
 				// 2: 3.59 / 1.27 / 3.61, 4: 3.61 / 1.32 / 3.69, 8: 3.92 / 1.47 / 4.07)
 
 // 48 warps per SM (40 registers): measured 32 / 40 / 48 / 64 warps per SM on church 4.06 / 3.46 / 3.20 / 3.35 ms (64 = 32
 // registers, spills)
+// ITEMS = candidate vertices per thread (tile = kFFBlock * ITEMS vertices): 4 where the launch still has several waves of
+// CTAs, fewer on small shards (ff_items_for below)
+template <int ITEMS>
 __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(DevScene S, FastState F) {
+	constexpr int kFFItems = ITEMS;
 	const int j = blockIdx.z;
+	if (blockIdx.x == 0 && blockIdx.y == 0 && j == 0 && threadIdx.x == 0) dbg_trace(F, 5);
 	if (j >= *F.ntodo) return;
 	const int row = F.todo[j], half = blockIdx.y;
 	__shared__ __align__(16) ShooterRec sh;
@@ -696,18 +715,28 @@ __global__ void __launch_bounds__(kFFBlock, 1536 / kFFBlock) ff_batch_kernel(Dev
 	}
 }
 
+// Vertices per thread for a launch over U vertices x 2 halves x rows: the largest of 4 / 2 / 1 that still gives four waves
+// of CTAs (12 CTAs per SM x 148 SMs); small shards (church on 8 GPUs: 13 k vertices per rank) otherwise end in a
+// nearly empty last wave.
+inline int ff_items_for(int U, int rows) {
+	for (int items = kFFItemsMax; items > 1; items >>= 1) {
+		const long long tiles = (U + kFFBlock * items - 1) / (kFFBlock * items);
+		if (tiles * 2 * rows >= 4ll * 12 * 148) return items;
+	}
+	return 1;
+}
+inline const void *ff_batch_fn(int items) {
+	return items >= 4 ? (const void *)ff_batch_kernel<4> : (items == 2 ? (const void *)ff_batch_kernel<2> : (const void *)ff_batch_kernel<1>);
+}
+
 // ---- form factors of the new rows at the candidates' own vertices ---------------------------------------
-// chain_kernel only needs the form factors between the candidates (a rows x rows x 3 table).  Those of rows cached
+// chain_kernel only needs the form factors BETWEEN the candidates (a rows x rows x 3 table).  Those of rows cached
 // in earlier rounds are in the cache already; those of the rows this round fills are computed here, ray by ray
 // (at most rows x rows x 3 x 2 rays, the same arithmetic as ff_batch_kernel: ff_geom + the bounded any-hit walk),
-// so that the chain - a single warp - runs concurrently with ff_batch_kernel instead of after it.
-// grid (ceil(rows * 6 / 128), rows); thread = (candidate i, vertex v, half) of todo entry blockIdx.y.
-__global__ void __launch_bounds__(128) ff_cand_kernel(DevScene S, FastState F) {
-	const int t = blockIdx.y;
-	if (t >= *F.ntodo) return;
-	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// so that the chain runs concurrently with ff_batch_kernel instead of after it.
+// Work item q of todo entry t = (candidate i, vertex v, half).
+__device__ void ff_cand_item(const DevScene &S, const FastState &F, int t, int q) {
 	const int i = q / 6, v = (q % 6) >> 1, half = q & 1;
-	if (i >= F.rows) return;
 	const int cslot = F.row_slot[i];
 	const int r = cslot >= 0 ? S.slot_to_recv[cslot] : -1;
 	if (r < 0) return;	// free row, or a candidate another rank owns
@@ -752,16 +781,37 @@ struct FFRows {	// form factor (both halves) of unique vertex u in cache row `ro
 constexpr int kChainPerLane = kMaxRows / 32;
 inline size_t chain_smem_bytes(int rows) { return (size_t)rows * sizeof(CandRec); }
 
-__global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
+// 512 threads x 128 registers = the whole register file of an SM: no ff_batch_kernel CTA shares the SM with the chain,
+// whose single warp otherwise got one issue slot in thirteen (measured 1.3 us per shot beside twelve ff_batch CTAs).
+constexpr int kChainGrid = 32;		// CTAs that share the candidates' rays; the last one to finish runs the chain
+constexpr int kChainBlock = 512;
+__global__ void __launch_bounds__(kChainBlock, 1) chain_kernel(DevScene S, FastState F) {
 	extern __shared__ __align__(16) unsigned char chain_smem[];
 	CandRec *cm = (CandRec *)chain_smem;
 	__shared__ int s_owned[kMaxRows];
 	__shared__ int s_ok;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int rows = F.rows;
+	// ---- phase 0 (all CTAs): the new rows' form factors at the candidates' vertices.  The kernel is launched on the side
+	// branch of the round with launch priority, so its CTAs are resident BEFORE ff_batch_kernel fills every SM (a
+	// stand-alone chain CTA - 128 registers per thread, ~80 KB of shared memory - did not fit beside twelve
+	// ff_batch CTAs per SM and only started when ff_batch_kernel had handed out its last wave).
+	{
+		__shared__ bool s_last;
+		if (blockIdx.x == 0 && threadIdx.x == 0) dbg_trace(F, 4);
+		const int nt = *F.ntodo, per = rows * 6;
+		for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nt * per; w += gridDim.x * blockDim.x) ff_cand_item(S, F, w / per, w % per);
+		__threadfence();
+		__syncthreads();
+		if (threadIdx.x == 0) s_last = atomicAdd(F.chain_ticket, 1u) == gridDim.x - 1;
+		__syncthreads();
+		if (!s_last) return;
+		__threadfence();
+		if (threadIdx.x == 0) *F.chain_ticket = 0u;
+	}
 	const unsigned long long round = *F.pred_round;
 	const int par = (int)(round & 1ull);
-	if (threadIdx.x == 0) s_ok = *F.error == 0;
+	if (threadIdx.x == 0) s_ok = *F.error == 0, dbg_trace(F, 6);
 	// own candidates: state, reflectance and the form factors of every filled row at their three vertices.  Three
 	// dependent round trips in all: directory -> receiver -> (state, vertex ids) -> form factors of every (candidate, row).
 	__shared__ int4 s_id[kMaxRows];
@@ -811,7 +861,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 	const int rec_words = (int)(offsetof(CandRec, fsum) / 4) + 3 * rows;
 	if (F.world > 1) {
 		// publish the owned records to every other rank (4-byte granules, one warp per record), then the sequence number
-		for (int i = warp; i < rows; i += 8) {
+		for (int i = warp; i < rows; i += (int)(blockDim.x >> 5)) {
 			if (!s_owned[i]) continue;
 			const int *src = (const int *)&cm[i];
 			for (int t = 0; t < F.world; t++) {
@@ -829,7 +879,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 		if (threadIdx.x < F.world && threadIdx.x != F.rank && s_ok && !peer_wait(&mine->cand_seq[par][threadIdx.x], round)) s_ok = 0;
 		__syncthreads();
 		if (s_ok) {
-			for (int i = warp; i < rows; i += 8) {
+			for (int i = warp; i < rows; i += (int)(blockDim.x >> 5)) {
 				if (s_owned[i] || F.row_slot[i] < 0) continue;
 				const volatile int *src = (const volatile int *)&mine->cand[par][i];
 				int *dst = (int *)&cm[i];
@@ -911,6 +961,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 		if (lane == 0) {
 			*F.nsched = k, *F.viol = k, *F.apply_ticket = 0u;
 			F.counters[2] += (unsigned long long)k;
+			dbg_trace(F, 7);
 		}
 		return;
 	}
@@ -987,6 +1038,7 @@ __global__ void __launch_bounds__(256) chain_kernel(DevScene S, FastState F) {
 	if (lane == 0) {
 		*F.nsched = k, *F.viol = k, *F.apply_ticket = 0u;
 		F.counters[2] += (unsigned long long)iters;
+		dbg_trace(F, 7);
 	}
 }
 
@@ -1011,6 +1063,7 @@ __global__ void __launch_bounds__(kApplyBlock, RADK_APPLY_MINB) apply_kernel(Dev
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int K = *F.nsched;
 	int n = K;
+	if (blockIdx.x == 0 && threadIdx.x == 0) dbg_trace(F, COMMIT ? 9 : 8);
 	if (COMMIT) {
 		if (threadIdx.x == 0) {
 			int v = *((volatile int *)F.viol);
@@ -1064,6 +1117,7 @@ __global__ void __launch_bounds__(kApplyBlock, RADK_APPLY_MINB) apply_kernel(Dev
 					const bool more = n > 0 && !*S.sel.converged && *F.budget > 0 && !*((volatile int *)F.error);
 					cudaGraphSetConditional((cudaGraphConditionalHandle)F.cond, more ? 1u : 0u);
 				}
+				if (F.dbg) dbg_trace(F, 10), F.dbg[15]++;
 			}
 		}
 		if (n >= K) return;	// the whole schedule was valid: the apply pass already wrote the right state

@@ -56,12 +56,31 @@ RADK_HD bool unsaturated(const float4 &a0, const float4 &a1, const float4 &a2) {
 	       a2.x < 255.0f || a2.y < 255.0f || a2.z < 255.0f;
 }
 
+// x / 3 (the `/ 3` of shade.cpp:247-249), correctly rounded without the division: q0 = x * RN(1/3), the residual
+// r = x - 3 q0 exactly (one FMA), q = RN(q0 + r * RN(1/3)).  Checked against x / 3.0f for ALL 2^32 float bit patterns
+// (tests/test_hostemu.py samples it; the exhaustive run takes 18 s): identical except -0 and +-inf, which are passed
+// through.  The IEEE division costs ~35 instructions on the device, three of them per receiver and shot (and per
+// candidate and shot in the chain's dependent loop).
+RADK_HD float div3(float x) {
+	const float y = 0.3333333432674407958984375f;	// RN(1/3) = 0x3eaaaaab
+	const float q0 = x * y;
+#if defined(__CUDA_ARCH__)
+	const float r = __fmaf_rn(-3.0f, q0, x);
+	const float q = __fmaf_rn(r, y, q0);
+	return (x == 0.0f || fabsf(x) == __int_as_float(0x7f800000)) ? x : q;
+#else
+	const float r = fmaf(-3.0f, q0, x);
+	const float q = fmaf(r, y, q0);
+	return (x == 0.0f || fabsf(x) == INFINITY) ? x : q;
+#endif
+}
+
 // CalRadiosity (shade.cpp:244-259) of one receiver: a_v = accB[v].rgb | deltaB[v]; ff_v = vertex form factors;
 // fk = Frgb * (0.5/255); sdB = the shooter's unshot energy.
 RADK_HD void apply_shot_ff(float4 &a0, float4 &a1, float4 &a2, float fkx, float fky, float fkz, float ff0, float ff1, float ff2,
 			   float sdB0, float sdB1, float sdB2) {
 	const float ff[3] = {ff0, ff1, ff2};
-	const float lo[3] = {fkx * sdB0 / 3, fky * sdB1 / 3, fkz * sdB2 / 3};	// shade.cpp:247-249
+	const float lo[3] = {div3(fkx * sdB0), div3(fky * sdB1), div3(fkz * sdB2)};	// shade.cpp:247-249: fk * dB / 3
 	float dB[3] = {a0.w, a1.w, a2.w};
 	float4 *acc[3] = {&a0, &a1, &a2};
 #if defined(__CUDA_ARCH__)

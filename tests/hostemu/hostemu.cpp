@@ -305,6 +305,20 @@ extern "C" void emu_shard_close(void *h) { delete (EmuShard *)h; }
 extern "C" int emu_shard_sizes(void *h, int *R, int *U) { EmuShard *e = (EmuShard *)h; *R = e->F.R, *U = e->F.U; return 0; }
 extern "C" void emu_shard_set_parallel_src(void *h, int P) { ((EmuShard *)h)->parallel_src = P < 1 ? 1 : P; }
 extern "C" long long emu_shard_count(void *h) { return ((EmuShard *)h)->local_count; }
+// div3 (shot_core.cuh) against the division it replaces: n patterns from `start` with stride `step`; returns mismatches
+extern "C" long long emu_div3_check(unsigned start, unsigned step, long long n) {
+	long long bad = 0;
+	unsigned u = start;
+	for (long long i = 0; i < n; i++, u += step) {
+		float x;
+		memcpy(&x, &u, 4);
+		if (x != x) continue;
+		volatile float xv = x;
+		const float a = xv / 3.0f, b = div3(x);
+		if (memcmp(&a, &b, 4) != 0) bad++;
+	}
+	return bad;
+}
 extern "C" int emu_shooter_rec_bytes(void) { return (int)sizeof(ShooterRec); }
 extern "C" int emu_cand_rec_bytes(void) { return (int)sizeof(CandRec); }
 
