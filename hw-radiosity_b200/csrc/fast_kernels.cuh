@@ -781,6 +781,66 @@ struct FFRows {	// form factor (both halves) of unique vertex u in cache row `ro
 constexpr int kChainPerLane = kMaxRows / 32;
 inline size_t chain_smem_bytes(int rows) { return (size_t)rows * sizeof(CandRec); }
 
+// The chain for a single shooter per iteration, CPL = candidates per lane actually in use (rows <= 32 CPL): the loops over a
+// lane's candidates are unrolled CPL times instead of kChainPerLane = 4 times (a third of the loop's instructions at
+// rows <= 64).  State arrays stay in registers (forceinline, constant indices).
+template <int CPL>
+__device__ __forceinline__ void chain_single(const DevScene &S, const FastState &F, const CandRec *cm, int lane, float4 (&a0)[kChainPerLane],
+					      float4 (&a1)[kChainPerLane], float4 (&a2)[kChainPerLane], const float (&fkx)[kChainPerLane],
+					      const float (&fky)[kChainPerLane], const float (&fkz)[kChainPerLane], const int (&slot)[kChainPerLane],
+					      unsigned long long (&key)[kChainPerLane]) {
+	// single shooter per iteration: the chain stays in registers (one shuffle round per shot)
+	const long long budget1 = *F.budget;
+	const int kmax = (int)(budget1 < (long long)kMaxChain ? (budget1 < 0 ? 0 : budget1) : (long long)kMaxChain);
+	auto lane_best = [&]() {
+		unsigned long long m = 0ull;
+#pragma unroll
+		for (int c = 0; c < CPL; c++) m = key[c] > m ? key[c] : m;
+		return m;
+	};
+	unsigned long long best = warp_max_u64(lane_best());
+	int k = 0;
+	while (best != 0ull && k < kmax) {
+		// the shooter: the lane that holds the best key (keys carry the slot, so non-zero keys are unique) and which of its candidates
+		int mine_c = -1;
+#pragma unroll
+		for (int c = 0; c < CPL; c++)
+			if (key[c] == best) mine_c = c;
+		const int bl = __ffs(__ballot_sync(0xffffffffu, mine_c >= 0)) - 1;
+		float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+		int ss = -1;
+#pragma unroll
+		for (int c = 0; c < CPL; c++)
+			if (c == mine_c) d0 = a0[c].w, d1 = a1[c].w, d2 = a2[c].w, ss = slot[c];
+		const int bc = __shfl_sync(0xffffffffu, mine_c, bl);
+		const int b = bl + 32 * bc;	// the shooter's candidate index = its cache row
+		const int sslot = __shfl_sync(0xffffffffu, ss, bl);
+		const float sd0 = __shfl_sync(0xffffffffu, d0, bl), sd1 = __shfl_sync(0xffffffffu, d1, bl), sd2 = __shfl_sync(0xffffffffu, d2, bl);
+#pragma unroll
+		for (int c = 0; c < CPL; c++) {
+			if (slot[c] < 0) continue;
+			if (slot[c] == sslot) a0[c].w = a1[c].w = a2[c].w = 0.0f;	// rad.cpp:446-449
+			else if (unsaturated(a0[c], a1[c], a2[c])) {
+				const float *f = cm[lane + 32 * c].fsum[b];
+				apply_shot_ff(a0[c], a1[c], a2[c], fkx[c], fky[c], fkz[c], f[0], f[1], f[2], sd0, sd1, sd2);
+			}
+			key[c] = energy_key(S.converge, a0[c].w, a1[c].w, a2[c].w, slot[c]);
+		}
+		best = warp_max_u64(lane_best());
+		if (lane == 0) {
+			ShotSched s;
+			s.slot = sslot, s.row = b, s.dB[0] = sd0, s.dB[1] = sd1, s.dB[2] = sd2, s.flags = kSchedHead | kSchedLast, s.next_key = best;
+			F.sched[k] = s;
+		}
+		k++;
+	}
+	if (lane == 0) {
+		*F.nsched = k, *F.viol = k, *F.apply_ticket = 0u;
+		F.counters[2] += (unsigned long long)k;
+		dbg_trace(F, 7);
+	}
+}
+
 // 512 threads x 128 registers = the whole register file of an SM: no ff_batch_kernel CTA shares the SM with the chain,
 // whose single warp otherwise got one issue slot in thirteen (measured 1.3 us per shot beside twelve ff_batch CTAs).
 constexpr int kChainGrid = 32;		// CTAs that share the candidates' rays; the last one to finish runs the chain
@@ -913,55 +973,11 @@ __global__ void __launch_bounds__(kChainBlock, 1) chain_kernel(DevScene S, FastS
 		key[c] = valid ? energy_key(S.converge, a0[c].w, a1[c].w, a2[c].w, slot[c]) : 0ull;
 	}
 	if (F.parallel_src <= 1) {
-		// single shooter per iteration: the chain stays in registers (one shuffle round per shot)
-		const long long budget1 = *F.budget;
-		const int kmax = (int)(budget1 < (long long)kMaxChain ? (budget1 < 0 ? 0 : budget1) : (long long)kMaxChain);
-		auto lane_best = [&]() {
-			unsigned long long m = 0ull;
-#pragma unroll
-			for (int c = 0; c < kChainPerLane; c++) m = key[c] > m ? key[c] : m;
-			return m;
-		};
-		unsigned long long best = warp_max_u64(lane_best());
-		int k = 0;
-		while (best != 0ull && k < kmax) {
-			// the shooter: the lane that holds the best key (keys carry the slot, so non-zero keys are unique) and which of its candidates
-			int mine_c = -1;
-#pragma unroll
-			for (int c = 0; c < kChainPerLane; c++)
-				if (key[c] == best) mine_c = c;
-			const int bl = __ffs(__ballot_sync(0xffffffffu, mine_c >= 0)) - 1;
-			float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-			int ss = -1;
-#pragma unroll
-			for (int c = 0; c < kChainPerLane; c++)
-				if (c == mine_c) d0 = a0[c].w, d1 = a1[c].w, d2 = a2[c].w, ss = slot[c];
-			const int bc = __shfl_sync(0xffffffffu, mine_c, bl);
-			const int b = bl + 32 * bc;	// the shooter's candidate index = its cache row
-			const int sslot = __shfl_sync(0xffffffffu, ss, bl);
-			const float sd0 = __shfl_sync(0xffffffffu, d0, bl), sd1 = __shfl_sync(0xffffffffu, d1, bl), sd2 = __shfl_sync(0xffffffffu, d2, bl);
-#pragma unroll
-			for (int c = 0; c < kChainPerLane; c++) {
-				if (slot[c] < 0) continue;
-				if (slot[c] == sslot) a0[c].w = a1[c].w = a2[c].w = 0.0f;	// rad.cpp:446-449
-				else if (unsaturated(a0[c], a1[c], a2[c])) {
-					const float *f = cm[lane + 32 * c].fsum[b];
-					apply_shot_ff(a0[c], a1[c], a2[c], fkx[c], fky[c], fkz[c], f[0], f[1], f[2], sd0, sd1, sd2);
-				}
-				key[c] = energy_key(S.converge, a0[c].w, a1[c].w, a2[c].w, slot[c]);
-			}
-			best = warp_max_u64(lane_best());
-			if (lane == 0) {
-				ShotSched s;
-				s.slot = sslot, s.row = b, s.dB[0] = sd0, s.dB[1] = sd1, s.dB[2] = sd2, s.flags = kSchedHead | kSchedLast, s.next_key = best;
-				F.sched[k] = s;
-			}
-			k++;
-		}
-		if (lane == 0) {
-			*F.nsched = k, *F.viol = k, *F.apply_ticket = 0u;
-			F.counters[2] += (unsigned long long)k;
-			dbg_trace(F, 7);
+		switch ((rows + 31) >> 5) {
+		case 1: chain_single<1>(S, F, cm, lane, a0, a1, a2, fkx, fky, fkz, slot, key); break;
+		case 2: chain_single<2>(S, F, cm, lane, a0, a1, a2, fkx, fky, fkz, slot, key); break;
+		case 3: chain_single<3>(S, F, cm, lane, a0, a1, a2, fkx, fky, fkz, slot, key); break;
+		default: chain_single<4>(S, F, cm, lane, a0, a1, a2, fkx, fky, fkz, slot, key); break;
 		}
 		return;
 	}
