@@ -58,7 +58,7 @@ RADK_HD bool unsaturated(const float4 &a0, const float4 &a1, const float4 &a2) {
 
 // x / 3 (the `/ 3` of shade.cpp:247-249), correctly rounded without the division: q0 = x * RN(1/3), the residual
 // r = x - 3 q0 exactly (one FMA), q = RN(q0 + r * RN(1/3)).  Checked against x / 3.0f for ALL 2^32 float bit patterns
-// (tests/test_hostemu.py samples it; the exhaustive run takes 18 s): identical except -0 and +-inf, which are passed
+// (the CPU test tier samples it, tests/hostemu; the exhaustive run takes 18 s): identical except -0 and +-inf, which are passed
 // through.  The IEEE division costs ~35 instructions on the device, three of them per receiver and shot (and per
 // candidate and shot in the chain's dependent loop).
 RADK_HD float div3(float x) {
