@@ -795,6 +795,7 @@ void radk_ctx_destroy(radk_ctx *c) {
 			for (int k = 0; k < 11; k++)
 				if (cnt[k]) fprintf(stderr, " %s %.1f", ev[k], sum[k] / cnt[k] / 1e3);
 			fprintf(stderr, " | gap to next round %.1f\n", ngap ? gap / ngap / 1e3 : 0.0);
+			fprintf(stderr, "[radk] top-64 selection self-check: %llu mismatches against the full sort in %llu rounds\n", t[14], rounds);
 		}
 	}
 	if (c->h_flags) cudaFreeHost(c->h_flags);

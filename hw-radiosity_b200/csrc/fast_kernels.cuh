@@ -231,6 +231,49 @@ __device__ void sort_keys_desc(unsigned long long *keys, int n) {
 		}
 }
 
+// The 64 largest of 2048 keys, sorted descending into keys[0 .. 64), by one CTA of 1024 threads (the rest of the array is
+// scratch afterwards).  Each warp sorts its 64 keys in registers (bitonic network on shuffles, no block barrier), then
+// five merge levels halve the number of runs: c[e] = max(a[e], b[63 - e]) is the top half of two descending runs as a
+// bitonic sequence, six more compare-exchange stages sort it.  11 block barriers instead of the 66 of the full sort.
+__device__ __forceinline__ void cmpx_desc(unsigned long long &x, int j, bool desc, int lane) {	// partner = lane ^ j, same register
+	const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+	const bool lower = (lane & j) == 0;
+	x = (lower == desc) ? (x > y ? x : y) : (x < y ? x : y);
+}
+__device__ void topk64_desc(unsigned long long *keys) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long x0 = keys[warp * 64 + lane], x1 = keys[warp * 64 + 32 + lane];	// elements e = lane and e = lane + 32 of the warp's run
+	__syncthreads();	// everybody has read its keys: the array is scratch from here on
+#pragma unroll
+	for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			// direction of element e: descending where (e & k) == 0; e & 32 is the register index
+			cmpx_desc(x0, j, k < 32 ? (lane & k) == 0 : true, lane);
+			cmpx_desc(x1, j, k < 32 ? (lane & k) == 0 : false, lane);
+		}
+	// k = 64 (all descending): j = 32 is the register pair of a lane, then the shuffles
+	if (x0 < x1) { const unsigned long long t = x0; x0 = x1, x1 = t; }
+#pragma unroll
+	for (int j = 16; j > 0; j >>= 1) cmpx_desc(x0, j, true, lane), cmpx_desc(x1, j, true, lane);
+	for (int stride = 1; stride < 32; stride <<= 1) {
+		keys[warp * 64 + lane] = x0, keys[warp * 64 + 32 + lane] = x1;
+		__syncthreads();
+		const bool active = (warp & (2 * stride - 1)) == 0;
+		unsigned long long p0 = 0ull, p1 = 0ull;
+		if (active) p0 = keys[(warp + stride) * 64 + 63 - lane], p1 = keys[(warp + stride) * 64 + 31 - lane];
+		__syncthreads();	// partners' runs are read before anybody overwrites its own
+		if (active) {
+			x0 = x0 > p0 ? x0 : p0, x1 = x1 > p1 ? x1 : p1;	// top 64 of the union, bitonic
+			if (x0 < x1) { const unsigned long long t = x0; x0 = x1, x1 = t; }
+#pragma unroll
+			for (int j = 16; j > 0; j >>= 1) cmpx_desc(x0, j, true, lane), cmpx_desc(x1, j, true, lane);
+		}
+	}
+	if (warp == 0) keys[lane] = x0, keys[32 + lane] = x1;
+	__syncthreads();
+}
+
 // Leaf masks of the new rows: which leaves list the shooter's original triangle.  One warp per row, all rows
 // in flight together (the chain todo -> record -> inverted index -> leaves is four dependent loads).
 __device__ void build_row_masks(const DevScene &S, const FastState &F, int nt) {
@@ -384,7 +427,21 @@ __global__ void __launch_bounds__(1024) predict_kernel(DevScene S, FastState F) 
 		F.group_key[q] = 0ull;	// ready for the next round
 	}
 	__syncthreads();
-	sort_keys_desc(keys, kPredictGroups);
+	if (F.parallel_src <= 1 && F.rows <= 64 && kPredictGroups == 2048) {
+		if (F.dbg) {	// RADK_DEBUG_PREDICT: self-check of the partial selection against the full sort, mismatches in dbg[14]
+			__shared__ unsigned long long full[kPredictGroups];
+			for (int q = threadIdx.x; q < kPredictGroups; q += blockDim.x) full[q] = keys[q];
+			__syncthreads();
+			sort_keys_desc(full, kPredictGroups);
+			topk64_desc(keys);
+			if (threadIdx.x < 64 && full[threadIdx.x] != keys[threadIdx.x]) atomicAdd(&F.dbg[14], 1ull);
+			__syncthreads();
+		} else {
+			topk64_desc(keys);
+		}
+	} else {
+		sort_keys_desc(keys, kPredictGroups);
+	}
 	if (F.parallel_src > 1) {
 		// group maxima can hide the 2nd .. P-th largest key behind a larger one of the same group: the exact pass
 		// (predict_exact_kernel) collects every key >= T = the P-th largest group maximum and finishes the round
