@@ -418,6 +418,25 @@ def run_ours(args):
                     cpu_shipped = None
         barrier()
         ctx.close()
+
+        # where a round's time goes (untimed, diagnostics build of the same kernels: %globaltimer stamps at the start / end
+        # of every kernel of a round, RADK_DEBUG_PREDICT): shows the chain running beside the form factors, the exchanges
+        timeline = None
+        try:
+            os.environ["RADK_DEBUG_PREDICT"] = "1"
+            dctx = rdist.sharded_context(model, rank, world, local_rank, **ckw)
+            os.environ.pop("RADK_DEBUG_PREDICT", None)
+            for _ in range(3):
+                dctx.rewind()
+                barrier()
+                dctx.step(cap)
+            timeline = dctx.round_timeline()
+            barrier()
+            dctx.close()
+        except Exception as e:          # diagnostics never take the headline line down
+            timeline = {"error": f"{type(e).__name__}: {e}"[:200]}
+        finally:
+            os.environ.pop("RADK_DEBUG_PREDICT", None)
         model.close()
 
         # the other BASELINE configs at this N (device time + parity flags), after the headline measurement
@@ -487,6 +506,7 @@ def run_ours(args):
                    "traced_rays_per_step": walk["traced_rays"], "l2": "flushed between steps (256 MiB write), state rewound on device",
                    "timing": "per-step CUDA-event windows around radk_ctx_step on its stream, mean of K steps",
                    "parity": "bit-exact mode (-fmad=false)"},
+        "round_timeline_us": timeline,
         "seconds_to_converge": ms_per_step / 1e3 if cap < 0 else None,
         "wall_s_timed_region": wall,
         "gpu_launches": launches,

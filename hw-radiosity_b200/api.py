@@ -66,7 +66,7 @@ EXPORTS = [
     "radk_model_write", "radk_model_write_colors", "radk_model_write_wait", "radk_model_format", "radk_ctx_create", "radk_ctx_destroy", "radk_ctx_reset",
     "radk_ctx_rewind", "radk_ctx_step", "radk_ctx_select", "radk_ctx_shoot", "radk_ctx_shooter_log", "radk_ctx_trinum",
     "radk_ctx_download", "radk_ctx_download_triangles", "radk_ctx_snapshot_colors", "radk_ctx_stats",
-    "radk_ctx_device_ms", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_ray_sees", "radk_vertex_ff",
+    "radk_ctx_device_ms", "radk_ctx_round_timeline", "radk_ctx_profile", "radk_ctx_sizes", "radk_ray_hitted", "radk_ray_sees", "radk_vertex_ff",
     "radk_ctx_peer_handle", "radk_ctx_peer_connect", "radk_ctx_peer_connect_local", "radk_ctx_owned_slots",
 ]
 
@@ -133,6 +133,7 @@ def load_library():
     L.radk_ctx_stats.argtypes = [vp, C.POINTER(Stats)]
     L.radk_ctx_device_ms.argtypes = [vp]
     L.radk_ctx_device_ms.restype = C.c_double
+    L.radk_ctx_round_timeline.argtypes = [vp, C.POINTER(C.c_double)]
     L.radk_ray_hitted.argtypes = [vp, vp, vp, vp, C.c_int, vp]
     L.radk_ray_sees.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
     L.radk_ctx_peer_handle.argtypes = [vp, vp]
@@ -347,6 +348,17 @@ class Context:
     @property
     def device_ms(self):
         return load_library().radk_ctx_device_ms(self._h)
+
+    def round_timeline(self):
+        """Mean start / end times (us after the round's start) of the kernels of a round, for contexts created with
+        RADK_DEBUG_PREDICT=1 in the environment; None otherwise."""
+        out = (C.c_double * 14)()
+        _check(load_library().radk_ctx_round_timeline(self._h, out))
+        if out[12] <= 0:
+            return None
+        names = ("predict", "predict_end", "merge", "merge_end", "candidate_rays", "ff_batch", "chain", "chain_end", "apply", "commit",
+                 "commit_end", "gap_to_next_round", "rounds", "top64_selfcheck_mismatches")
+        return {n: round(out[i], 1) for i, n in enumerate(names) if out[i] >= 0}
 
     # ---- multi-GPU introductions -----------------------------------------------------------
     def peer_handle(self):

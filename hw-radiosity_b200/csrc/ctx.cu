@@ -724,6 +724,35 @@ int read_flags(radk_ctx *c) {
 	return RADK_OK;
 }
 
+// RADK_DEBUG_PREDICT: mean time (us, after the round's predict start) of the round's events over the last <= 64 rounds;
+// out[0..10] = the events of dbg_trace (fast_kernels.cuh), out[11] = median gap from the commit's bookkeeping to the next
+// round's start, out[12] = rounds averaged, out[13] = mismatches of the top-64 selection self-check.  -1: not recorded.
+int round_timeline(radk_ctx *c, double out[14]) {
+	for (int k = 0; k < 14; k++) out[k] = -1.0;
+	if (!c->dbg.p) return RADK_OK;
+	std::vector<unsigned long long> t(16 + 64 * 16);
+	CUDA_TRY(cudaMemcpy(t.data(), c->dbg.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	const int nr = (int)std::min<unsigned long long>(t[15], 64);
+	double sum[11] = {0};
+	int cnt[11] = {0};
+	std::vector<double> gaps;
+	for (int r = 0; r < nr; r++) {
+		const unsigned long long *q = t.data() + 16 + 16 * r;
+		for (int k = 0; k < 11; k++)
+			if (q[0] && q[k] >= q[0] && q[k] - q[0] < 100000000ull) sum[k] += (double)(q[k] - q[0]), cnt[k]++;
+		const unsigned long long *nx = t.data() + 16 + 16 * ((r + 1) % 64);
+		if (nx[0] > q[10] && nx[0] - q[10] < 1000000ull) gaps.push_back((double)(nx[0] - q[10]));
+	}
+	for (int k = 0; k < 11; k++)
+		if (cnt[k]) out[k] = sum[k] / cnt[k] / 1e3;
+	if (!gaps.empty()) {	// the median: the gap between two steps (host work) is not a round-to-round gap
+		std::sort(gaps.begin(), gaps.end());
+		out[11] = gaps[gaps.size() / 2] / 1e3;
+	}
+	out[12] = nr, out[13] = (double)t[14];
+	return RADK_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -778,23 +807,15 @@ void radk_ctx_destroy(radk_ctx *c) {
 		if (cudaMemcpy(t, c->dbg.p, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess) {
 			fprintf(stderr, "[radk] predict phases (ns): scan+ticket %llu, top-K %llu, cache rebuild %llu, shooter records %llu, leaf masks %llu\n",
 				t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
-			// timeline of the last (up to 64) rounds, relative to the round's predict start; then the gap to the next round
 			static const char *ev[11] = {"predict", "predict_end", "merge", "merge_end", "ff_cand", "ff_batch", "chain", "chain_end", "apply", "commit", "commit_end"};
-			const unsigned long long rounds = t[15];
-			double sum[11] = {0}, gap = 0;
-			int cnt[11] = {0}, ngap = 0;
-			const int nr = (int)std::min<unsigned long long>(rounds, 64);
-			for (int r = 0; r < nr; r++) {
-				const unsigned long long *q = t + 16 + 16 * r;
+			double tl[14];
+			if (round_timeline(c, tl) == RADK_OK) {
+				fprintf(stderr, "[radk] round timeline, mean us after the round's predict start (rank %d, %d rounds):", c->opt.rank, (int)tl[12]);
 				for (int k = 0; k < 11; k++)
-					if (q[k] >= q[0] && q[k] - q[0] < 100000000ull && q[0]) sum[k] += (double)(q[k] - q[0]), cnt[k]++;
-				const unsigned long long *nx = t + 16 + 16 * ((r + 1) % 64);
-				if (r + 1 < nr && nx[0] > q[10] && nx[0] - q[10] < 1000000ull) gap += (double)(nx[0] - q[10]), ngap++;
+					if (tl[k] >= 0) fprintf(stderr, " %s %.1f", ev[k], tl[k]);
+				fprintf(stderr, " | gap to next round %.1f\n", tl[11]);
 			}
-			fprintf(stderr, "[radk] round timeline, mean us after the round's predict start (rank %d, %d rounds):", c->opt.rank, nr);
-			for (int k = 0; k < 11; k++)
-				if (cnt[k]) fprintf(stderr, " %s %.1f", ev[k], sum[k] / cnt[k] / 1e3);
-			fprintf(stderr, " | gap to next round %.1f\n", ngap ? gap / ngap / 1e3 : 0.0);
+			const unsigned long long rounds = t[15];
 			fprintf(stderr, "[radk] top-64 selection self-check: %llu mismatches against the full sort in %llu rounds\n", t[14], rounds);
 		}
 	}
@@ -1212,6 +1233,13 @@ int radk_ctx_stats(radk_ctx *c, radk_stats *out) {
 }
 
 double radk_ctx_device_ms(const radk_ctx *c) { return c ? c->device_ms : 0.0; }
+
+int radk_ctx_round_timeline(radk_ctx *c, double out[14]) {
+	if (!c || !out) { set_error("radk_ctx_round_timeline: null argument"); return RADK_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return round_timeline(c, out);
+}
 
 int radk_ctx_shoot(radk_ctx *c, const int *slots, int n) {
 	if (c && c->split_mode) { set_error("radk_ctx_shoot: not available on adaptive-split contexts"); return RADK_ERR_STATE; }

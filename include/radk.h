@@ -196,6 +196,12 @@ int radk_ctx_snapshot_colors(radk_ctx *c, int *rgb, int trinum);
 int radk_ctx_stats(radk_ctx *c, radk_stats *st);
 /* Device time (ms, CUDA events on the context's stream) spent inside radk_ctx_step so far. */
 double radk_ctx_device_ms(const radk_ctx *c);
+/* Diagnostics (contexts created with RADK_DEBUG_PREDICT=1 in the environment; -1 everywhere otherwise): mean time in us,
+ * after the start of a round of the batched loop, at which each of its kernels started / ended, over the last <= 64
+ * rounds - out[0..10] = predict start, predict end, merge start, merge end, candidates' rays start, form factors start,
+ * chain start, chain end, apply start, commit start, commit's bookkeeping done; out[11] = median gap to the next round;
+ * out[12] = rounds averaged; out[13] = mismatches of the top-64 selection self-check.  No counterpart in the reference. */
+int radk_ctx_round_timeline(radk_ctx *c, double out[14]);
 /* Profiling aid: runs up to max_shots shots (max_shots < 0: to convergence) with a CUDA-event pair
  * around every kernel launch on the context's stream and accumulates device time per kernel class:
  *   ms[0]/n[0] selection   (predict_kernel, or select_kernel on the per-shot path)

@@ -148,3 +148,21 @@ def test_non_power_of_two_grid_does_not_hang(hr, po):
     """GridNum = 63: the reference's RayHitted can bounce between two leaves forever on such a scene; the
     device cuts the walk (kMaxWalkSteps) and the oracle applies the same cut, so they still agree."""
     check_synthetic(hr, po, 1000000, False)
+
+
+def test_round_timeline_and_top64_selection_self_check(hr, models_dir, monkeypatch):
+    """Diagnostics build of the round (RADK_DEBUG_PREDICT): the top-64 selection of predict_kernel (registers + shuffles)
+    agrees with the full sort in every round, and the timeline shows the chain running BESIDE the form factors (it ends
+    before the apply pass starts, and starts long before the form factors can have finished)."""
+    monkeypatch.setenv("RADK_DEBUG_PREDICT", "1")
+    m = hr.Model(str(models_dir / "box.tri"))
+    ctx = hr.Context(m)
+    monkeypatch.delenv("RADK_DEBUG_PREDICT")
+    done, conv = ctx.step(1500)
+    assert done == 1500
+    t = ctx.round_timeline()
+    assert t is not None and t["rounds"] >= 10
+    assert t["top64_selfcheck_mismatches"] == 0
+    assert t["predict_end"] < t["ff_batch"] and t["candidate_rays"] <= t["chain"] < t["chain_end"] <= t["apply"] < t["commit"]
+    plain = hr.Context(m)
+    assert plain.round_timeline() is None
