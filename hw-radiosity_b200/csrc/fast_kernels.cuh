@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(1024) predict_exact_kernel(DevScene S, FastSta
 // Multi-GPU second half of the prediction (one CTA of 1024 threads): wait for every rank's candidates,
 // take the global top `rows`, rebuild the cache (identically on every rank), adopt the shooter records.
 __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastState F) {
-	__shared__ unsigned long long keys[kMaxWorld * kMaxRows];
+	static_assert(kMaxWorld * kMaxRows == 1024, "one mailed candidate per thread");
+	__shared__ unsigned long long keys[2 * kMaxWorld * kMaxRows];	// upper half: zero padding for the 2048-key partial selection
 	__shared__ int top_src[kMaxRows];
 	__shared__ CacheScratch cs;
 	__shared__ int s_ok;
@@ -546,18 +547,21 @@ __global__ void __launch_bounds__(1024) predict_merge_kernel(DevScene S, FastSta
 	const int src = threadIdx.x / kMaxRows, j = threadIdx.x % kMaxRows;
 	unsigned long long k0 = 0ull;
 	if (src < F.world && j < rows) k0 = *((volatile unsigned long long *)&mine->pred[par][src][j].key);
-	keys[threadIdx.x] = k0;
+	keys[threadIdx.x] = k0, keys[kMaxWorld * kMaxRows + threadIdx.x] = 0ull;
 	if (threadIdx.x < kMaxRows) top_src[threadIdx.x] = 0;
 	__syncthreads();
-	sort_keys_desc(keys, kMaxWorld * kMaxRows);
+	// up to 64 rows: the 64 largest in registers (topk64_desc) instead of the full sort of the 1024 mailed keys
+	const bool partial = rows <= 64;
+	if (partial) topk64_desc(keys);
+	else sort_keys_desc(keys, kMaxWorld * kMaxRows);
 	const unsigned long long *top = keys;
-	if (k0 != 0ull) {	// where did my key end up?  (binary search in the descending order)
-		int lo = 0, hi = kMaxWorld * kMaxRows - 1;
+	if (k0 != 0ull) {	// where did my key end up?  (binary search in the descending part)
+		int lo = 0, hi = (partial ? 64 : kMaxWorld * kMaxRows) - 1;
 		while (lo < hi) {
 			const int mid = (lo + hi) >> 1;
 			if (top[mid] > k0) lo = mid + 1; else hi = mid;
 		}
-		if (lo < rows) top_src[lo] = threadIdx.x;
+		if (lo < rows && top[lo] == k0) top_src[lo] = threadIdx.x;
 	}
 	__syncthreads();
 	const int nt = rebuild_cache(F, top, cs);
