@@ -3,6 +3,8 @@
 // file-statics raycast.cpp:9-16) as one object instead of globals.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
@@ -19,8 +21,57 @@ constexpr int kRefMaxTreeNode = 20000;		// rad.h:11
 constexpr int kMaxTriPerNode = 10;		// rad.h:12
 constexpr int kMaxLevel = 6;			// rad.h:7
 
+// The slot store (the reference's static TriStore[], rad.cpp:33): malloc-backed so that PrePartition can refine in a
+// calloc'ed pool (never-written slots stay untouched zero pages, like the reference's BSS) and simply hand the pool
+// over - copying 5 GB of records into a vector was a fifth of the set-up of an 11.6 M-receiver scene.
+class TriBuf {
+public:
+	TriBuf() = default;
+	TriBuf(const TriBuf &) = delete;
+	TriBuf &operator=(const TriBuf &) = delete;
+	~TriBuf() { free(p_); }
+	radk_triangle *data() { return p_; }
+	const radk_triangle *data() const { return p_; }
+	size_t size() const { return n_; }
+	radk_triangle &operator[](size_t i) { return p_[i]; }
+	const radk_triangle &operator[](size_t i) const { return p_[i]; }
+	void clear() { n_ = 0; }
+	bool reserve(size_t cap) {
+		if (cap <= cap_) return true;
+		void *q = realloc(p_, cap * sizeof(radk_triangle));
+		if (!q) return false;
+		p_ = (radk_triangle *)q, cap_ = cap;
+		return true;
+	}
+	void push_back(const radk_triangle &t) {
+		if (n_ == cap_ && !reserve(cap_ ? 2 * cap_ : 1024)) abort();
+		p_[n_++] = t;
+	}
+	void assign(const radk_triangle *b, const radk_triangle *e) {
+		const size_t n = (size_t)(e - b);
+		if (!reserve(n)) abort();
+		memcpy(p_, b, n * sizeof(radk_triangle));
+		n_ = n;
+	}
+	void resize(size_t n) {	// new slots are zero, like the reference's BSS
+		if (n > cap_ && !reserve(n)) abort();
+		if (n > n_) memset((void *)(p_ + n_), 0, (n - n_) * sizeof(radk_triangle));
+		n_ = n;
+	}
+	void shrink_to_fit() {
+		if (n_ < cap_ && n_ > 0) {
+			void *q = realloc(p_, n_ * sizeof(radk_triangle));
+			if (q) p_ = (radk_triangle *)q, cap_ = n_;
+		}
+	}
+	void adopt(radk_triangle *p, size_t n, size_t cap) { free(p_); p_ = p, n_ = n, cap_ = cap; }	// takes a malloc / calloc block
+private:
+	radk_triangle *p_ = nullptr;
+	size_t n_ = 0, cap_ = 0;
+};
+
 struct Model {
-	std::vector<radk_triangle> tri;		// size() == capacity of the pool; live slots [0, trinum)
+	TriBuf tri;				// live slots [0, trinum)
 	int trinum = 0;
 	int n0 = 0;
 	float G0[3] = {0, 0, 0}, G1[3] = {0, 0, 0};

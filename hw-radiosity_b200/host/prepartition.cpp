@@ -9,9 +9,17 @@
 //    previous contents (zero for never-used slots);
 //  * the cross-link test at shade.cpp:416 compares array addresses and is therefore always false.
 #include <algorithm>
+#include <cstdint>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 #include <cstdlib>
 #include <cstring>
-#include <queue>
+#include <functional>
+#include <iterator>
+#include <map>
+#include <set>
+#include <vector>
 #include <utility>
 #include "model.hpp"
 
@@ -143,24 +151,66 @@ void prepartition(Model &m) {
 	const size_t cap = (size_t)std::max(limit, m.trinum);
 	radk_triangle *pool = (radk_triangle *)calloc(cap, sizeof(radk_triangle));
 	if (!pool) return;	// out of memory: the mesh stays unrefined
+#if defined(__linux__)
+	{	// a multi-GB pool walked in priority order: ask for huge pages (advice only; the block stays calloc's)
+		const uintptr_t a = ((uintptr_t)pool + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1), e = ((uintptr_t)pool + cap * sizeof(radk_triangle)) & ~(uintptr_t)((2u << 20) - 1);
+		if (e > a) madvise((void *)a, e - a, MADV_HUGEPAGE);
+	}
+#endif
 	memcpy(pool, m.tri.data(), (size_t)m.trinum * sizeof(radk_triangle));
 	Splitter sp{m, pool};
-	// The reference keeps its work list in a std::set<pair<area, slot>> and takes *rbegin().  A binary heap pops the
-	// same sequence as long as the set never has to merge two equal pairs - and it never does: a slot is only pushed
-	// again when one of its children takes its place, with exactly half the area it had at its previous push, so all
-	// entries of one slot differ in area (fresh slots are pushed once).
-	std::priority_queue<std::pair<float, int>> work;
+	// The reference keeps its work list in a std::set<pair<area, slot>> and takes *rbegin(): largest area first, larger
+	// slot on ties.  Almost every push made while a triangle is split carries HALF of an area that is already in the list
+	// ((float)((double)area / 2.0)), i.e. it belongs behind everything of the area being processed: the list is a map
+	// area -> slots whose largest bucket is loaded, sorted once (descending) and walked.  The rare push that does not
+	// go behind (the co-split children of a neighbour that was never listed, e.g. a light) lands in a small ordered
+	// set that is consulted at every pop.  Same pop sequence as the set (pairs are unique: entries of one slot always
+	// differ in area, fresh slots are pushed once), without a 23 M-entry heap whose sift-downs miss the cache.
+	struct WorkList {
+		std::map<float, std::vector<int>> later;	// areas below the loaded bucket
+		std::vector<int> bucket;			// the loaded bucket, slots descending
+		size_t bi = 0;
+		float bucket_area = 0.0f;
+		bool loaded = false;
+		std::set<std::pair<float, int>> hot;		// pushes at or above the loaded bucket's area
+
+		void push(float a, int slot) {
+			if (loaded && !(a < bucket_area)) hot.insert(std::make_pair(a, slot));
+			else later[a].push_back(slot);
+		}
+		bool pop(std::pair<float, int> &out) {
+			if (bi >= bucket.size()) {
+				loaded = false;
+				if (!later.empty()) {
+					auto last = std::prev(later.end());
+					bucket_area = last->first;
+					bucket.clear();
+					bucket.swap(last->second);
+					later.erase(last);
+					std::sort(bucket.begin(), bucket.end(), std::greater<int>());
+					bi = 0, loaded = true;
+				}
+			}
+			const bool hb = loaded && bi < bucket.size(), hh = !hot.empty();
+			if (!hb && !hh) return false;
+			if (hh && (!hb || *hot.rbegin() > std::make_pair(bucket_area, bucket[bi]))) {
+				out = *hot.rbegin();
+				hot.erase(std::prev(hot.end()));
+			} else {
+				out = std::make_pair(bucket_area, bucket[bi++]);
+			}
+			return true;
+		}
+	} work;
 	for (int i = 0; i < m.trinum; i++) {
 		const radk_triangle &t = pool[i];
 		if (t.area < 1.f || is_light(t)) continue;
-		work.push(std::make_pair(t.area, i));
+		work.push(t.area, i);
 	}
-	while (!work.empty()) {		// the reference dereferences rbegin() of an empty set here (UB)
-		const std::pair<float, int> top = work.top();
-		work.pop();
+	const bool exhaustive = m.opts.prepartition == 2;	// synthetic scaling scenes only: keep going where the reference gives up
+	std::pair<float, int> top;
+	while (work.pop(top)) {		// the reference dereferences rbegin() of an empty set here (UB)
 		const int slot = top.second;
-		// opts.prepartition == 2 (synthetic scaling scenes only): keep going where the reference gives up
-		const bool exhaustive = m.opts.prepartition == 2;
 		if (pool[slot].area < 1) { if (exhaustive) continue; break; }
 		int child[4];
 		if (sp.split(slot, child) < 0) { if (exhaustive && !sp.pool_full(4)) continue; break; }
@@ -177,10 +227,9 @@ void prepartition(Model &m) {
 			}
 		}
 		for (int i = 0; i < 4; i++)
-			if (child[i] >= 0) work.push(std::make_pair(pool[child[i]].area, child[i]));
+			if (child[i] >= 0) work.push(pool[child[i]].area, child[i]);
 	}
-	m.tri.assign(pool, pool + m.trinum);
-	free(pool);
+	m.tri.adopt(pool, (size_t)m.trinum, cap);	// the pool becomes the store (trimmed by the caller's shrink_to_fit)
 }
 
 }  // namespace radk
