@@ -185,9 +185,14 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 				      (t.p[0][2] + t.p[1][2] + t.p[2][2]) / 3};
 		lkey[i] = ((uint64_t)(uint32_t)t.parent << 32) | morton(cen);
 	}
+	// (key, position in `leaves`) pairs sorted directly (leaves is ascending, so the position breaks ties like the slot
+	// does): an index sort through a comparator that chases two arrays took three times as long on 11.6 M receivers
+	std::vector<std::pair<uint64_t, int>> lsort(leaves.size());
+	for (size_t i = 0; i < leaves.size(); i++) lsort[i] = std::make_pair(lkey[i], (int)i);
+	std::sort(lsort.begin(), lsort.end());
 	std::vector<int> order(leaves.size());
-	std::iota(order.begin(), order.end(), 0);
-	std::sort(order.begin(), order.end(), [&](int a, int b) { return lkey[a] != lkey[b] ? lkey[a] < lkey[b] : leaves[a] < leaves[b]; });
+	for (size_t i = 0; i < leaves.size(); i++) order[i] = lsort[i].second;
+	std::vector<std::pair<uint64_t, int>>().swap(lsort);
 	F.leaves_total = (int)leaves.size();
 	if (world < 1) world = 1;
 	// block-cyclic sharding of the sorted receivers: blocks of kShardBlock neighbours are dealt round-robin, so
@@ -234,27 +239,35 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 	}
 
 	// ---- unique (vertex, parent) pairs of this shard, sorted by (parent, Morton)
-	std::unordered_map<VKey, int, VKeyHash> seen;
-	seen.reserve((size_t)R * 2);
+	// open-addressing table of vertex ids (keys compared through ukeys[]): ids are handed out in order of first
+	// appearance, like the node-based map this replaces (which spent its time in malloc and pointer chasing)
+	size_t tcap = 1024;
+	while (tcap < (size_t)R * 4) tcap <<= 1;	// load factor <= 0.75 even if no vertex is shared
+	std::vector<int> table(tcap, -1);
+	const size_t tmask = tcap - 1;
 	std::vector<VKey> ukeys;
 	std::vector<float4> upos;
+	ukeys.reserve((size_t)R), upos.reserve((size_t)R);
 	F.vid.resize(R);
+	const VKeyHash vhash;
 	for (int r = 0; r < R; r++) {
 		int ids[3];
 		for (int v = 0; v < 3; v++) {
 			const float4 &gp = F.geo[v][r];
 			// exact bit patterns: p enters the arithmetic by value, so -0/+0 are not merged
 			const VKey k{fbits(gp.x), fbits(gp.y), fbits(gp.z), F.recv_parent[r]};
-			auto it = seen.find(k);
-			if (it == seen.end()) {
-				it = seen.emplace(k, (int)ukeys.size()).first;
+			size_t h = vhash(k) & tmask;
+			while (table[h] >= 0 && !(ukeys[table[h]] == k)) h = (h + 1) & tmask;
+			if (table[h] < 0) {
+				table[h] = (int)ukeys.size();
 				ukeys.push_back(k);
 				upos.push_back(f4(gp.x, gp.y, gp.z, ibits(F.recv_parent[r])));
 			}
-			ids[v] = it->second;
+			ids[v] = table[h];
 		}
 		F.vid[r] = i4(ids[0], ids[1], ids[2], F.recv_parent[r]);
 	}
+	std::vector<int>().swap(table);
 	const int U = (int)ukeys.size();
 	F.U = U;
 	std::vector<uint64_t> ukey2(U);
@@ -269,8 +282,12 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 		}
 	}
 	std::vector<int> uorder(U), unew(U);
-	std::iota(uorder.begin(), uorder.end(), 0);
-	std::sort(uorder.begin(), uorder.end(), [&](int a, int b) { return ukey2[a] != ukey2[b] ? ukey2[a] < ukey2[b] : a < b; });
+	{
+		std::vector<std::pair<uint64_t, int>> usort(U);
+		for (int u = 0; u < U; u++) usort[u] = std::make_pair(ukey2[u], u);
+		std::sort(usort.begin(), usort.end());
+		for (int u = 0; u < U; u++) uorder[u] = usort[u].second;
+	}
 	F.uv.resize(U);
 	for (int i = 0; i < U; i++) unew[uorder[i]] = i, F.uv[i] = upos[uorder[i]];
 	{
