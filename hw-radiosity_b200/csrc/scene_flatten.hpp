@@ -9,6 +9,7 @@
 #include <numeric>
 #include <string>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "radk.h"
@@ -80,6 +81,18 @@ inline float ibits(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline float4 f4(float a, float b, float c, float d) { float4 r; r.x = a, r.y = b, r.z = c, r.w = d; return r; }
 inline int4 i4(int a, int b, int c, int d) { int4 r; r.x = a, r.y = b, r.z = c, r.w = d; return r; }
 }  // namespace flat_detail
+
+// Set-up passes over millions of 236-byte records are memory bound and independent per record: a few host threads share
+// them (the results do not depend on the number of threads).
+template <typename Fn> inline void flat_parallel(size_t n, Fn fn) {
+	const unsigned hw = std::thread::hardware_concurrency();
+	const size_t nt = n < 200000 ? 1 : std::min<size_t>(8, std::max(1u, hw));
+	if (nt <= 1) { fn((size_t)0, n, 0); return; }
+	std::vector<std::thread> th;
+	const size_t chunk = (n + nt - 1) / nt;
+	for (size_t t = 0; t < nt; t++) th.emplace_back([=] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk), (int)t); });
+	for (auto &x : th) x.join();
+}
 
 // Returns a RADK_* code; on failure F.error holds the message.
 inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F) {
@@ -179,12 +192,14 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 		return spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
 	};
 	std::vector<uint64_t> lkey(leaves.size());
-	for (size_t i = 0; i < leaves.size(); i++) {
-		const radk_triangle &t = s->tri[leaves[i]];
-		const float cen[3] = {(t.p[0][0] + t.p[1][0] + t.p[2][0]) / 3, (t.p[0][1] + t.p[1][1] + t.p[2][1]) / 3,
-				      (t.p[0][2] + t.p[1][2] + t.p[2][2]) / 3};
-		lkey[i] = ((uint64_t)(uint32_t)t.parent << 32) | morton(cen);
-	}
+	flat_parallel(leaves.size(), [&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; i++) {
+			const radk_triangle &t = s->tri[leaves[i]];
+			const float cen[3] = {(t.p[0][0] + t.p[1][0] + t.p[2][0]) / 3, (t.p[0][1] + t.p[1][1] + t.p[2][1]) / 3,
+					      (t.p[0][2] + t.p[1][2] + t.p[2][2]) / 3};
+			lkey[i] = ((uint64_t)(uint32_t)t.parent << 32) | morton(cen);
+		}
+	});
 	// (key, position in `leaves`) pairs sorted directly (leaves is ascending, so the position breaks ties like the slot
 	// does): an index sort through a comparator that chases two arrays took three times as long on 11.6 M receivers
 	std::vector<std::pair<uint64_t, int>> lsort(leaves.size());
@@ -212,31 +227,52 @@ inline int flatten_scene(const radk_scene *s, int rank, int world, FlatScene &F)
 	F.par_fk.assign(s->n0, f4(0, 0, 0, 0));
 	// per-original tables cover every original (also those whose receivers live on other ranks):
 	// a shooter owned elsewhere still needs its normal here.
-	std::vector<char> par_seen(s->n0, 0);
 	const float kref = (float)(0.5 / 255.0);	// shade.cpp:246
-	for (size_t i = 0; i < leaves.size(); i++) {
-		const radk_triangle &t = s->tri[leaves[i]];
-		const float nlen = sqrtf(t.n[0] * t.n[0] + t.n[1] * t.n[1] + t.n[2] * t.n[2]);
-		const float4 pn = f4(t.n[0], t.n[1], t.n[2], nlen);
-		const float4 fk = f4(t.Frgb[0] * kref, t.Frgb[1] * kref, t.Frgb[2] * kref, 0.f);
-		if (!par_seen[t.parent]) {
-			par_seen[t.parent] = 1, F.par_n[t.parent] = pn, F.par_fk[t.parent] = fk;
-		} else if (memcmp(&F.par_n[t.parent], &pn, 12) != 0 || memcmp(&F.par_fk[t.parent], &fk, 12) != 0) {
+	{
+		// every thread notes, per original, the first normal / reflectance it meets in its range and checks the rest of
+		// its range against it; the per-thread tables are then checked against each other
+		struct Seen { std::vector<char> seen; std::vector<float4> n, fk; bool bad = false; };
+		std::vector<Seen> part(8);
+		for (auto &q : part) q.seen.assign(s->n0, 0), q.n.assign(s->n0, f4(0, 0, 0, 0)), q.fk.assign(s->n0, f4(0, 0, 0, 0));
+		flat_parallel(leaves.size(), [&](size_t b, size_t e, int tid) {
+			Seen &q = part[tid];
+			for (size_t i = b; i < e; i++) {
+				const radk_triangle &t = s->tri[leaves[i]];
+				const float nlen = sqrtf(t.n[0] * t.n[0] + t.n[1] * t.n[1] + t.n[2] * t.n[2]);
+				const float4 pn = f4(t.n[0], t.n[1], t.n[2], nlen);
+				const float4 fk = f4(t.Frgb[0] * kref, t.Frgb[1] * kref, t.Frgb[2] * kref, 0.f);
+				if (!q.seen[t.parent]) q.seen[t.parent] = 1, q.n[t.parent] = pn, q.fk[t.parent] = fk;
+				else if (memcmp(&q.n[t.parent], &pn, 12) != 0 || memcmp(&q.fk[t.parent], &fk, 12) != 0) q.bad = true;
+			}
+		});
+		std::vector<char> par_seen(s->n0, 0);
+		bool bad = false;
+		for (auto &q : part) {
+			bad = bad || q.bad;
+			for (int o = 0; o < s->n0; o++) {
+				if (!q.seen[o]) continue;
+				if (!par_seen[o]) par_seen[o] = 1, F.par_n[o] = q.n[o], F.par_fk[o] = q.fk[o];
+				else if (memcmp(&F.par_n[o], &q.n[o], 12) != 0 || memcmp(&F.par_fk[o], &q.fk[o], 12) != 0) bad = true;
+			}
+		}
+		if (bad) {
 			F.error = "receivers of one original disagree on normal/reflectance: not a mesh produced by PrePartitionTriangles";
 			return RADK_ERR_STATE;
 		}
 	}
-	for (int r = 0; r < R; r++) {
-		const int slot = leaves[order[mine[r]]];
-		const radk_triangle &t = s->tri[slot];
-		F.recv_slot[r] = slot;
-		F.recv_parent[r] = t.parent;
-		F.slot_to_recv[slot] = r;
-		F.geo[0][r] = f4(t.p[0][0], t.p[0][1], t.p[0][2], ibits(t.parent));
-		F.geo[1][r] = f4(t.p[1][0], t.p[1][1], t.p[1][2], ibits(slot));
-		F.geo[2][r] = f4(t.p[2][0], t.p[2][1], t.p[2][2], t.area);
-		for (int v = 0; v < 3; v++) F.st[v][r] = f4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
-	}
+	flat_parallel((size_t)R, [&](size_t b, size_t e, int) {
+		for (size_t r = b; r < e; r++) {
+			const int slot = leaves[order[mine[r]]];
+			const radk_triangle &t = s->tri[slot];
+			F.recv_slot[r] = slot;
+			F.recv_parent[r] = t.parent;
+			F.slot_to_recv[slot] = (int)r;
+			F.geo[0][r] = f4(t.p[0][0], t.p[0][1], t.p[0][2], ibits(t.parent));
+			F.geo[1][r] = f4(t.p[1][0], t.p[1][1], t.p[1][2], ibits(slot));
+			F.geo[2][r] = f4(t.p[2][0], t.p[2][1], t.p[2][2], t.area);
+			for (int v = 0; v < 3; v++) F.st[v][r] = f4(t.accB[v][0], t.accB[v][1], t.accB[v][2], t.deltaB[v]);
+		}
+	});
 
 	// ---- unique (vertex, parent) pairs of this shard, sorted by (parent, Morton)
 	// open-addressing table of vertex ids (keys compared through ukeys[]): ids are handed out in order of first
