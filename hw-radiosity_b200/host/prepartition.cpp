@@ -164,7 +164,8 @@ void prepartition(Model &m) {
 	// ((float)((double)area / 2.0)), i.e. it belongs behind everything of the area being processed: the list is a map
 	// area -> slots whose largest bucket is loaded, sorted once (descending) and walked.  The rare push that does not
 	// go behind (the co-split children of a neighbour that was never listed, e.g. a light) lands in a small ordered
-	// set that is consulted at every pop.  Same pop sequence as the set (pairs are unique: entries of one slot always
+	// set that is consulted at every pop (church: 82 such pushes, hall 100, sbox 412 - the byte-identical meshes of the ten
+	// models cover it).  Same pop sequence as the set (pairs are unique: entries of one slot always
 	// differ in area, fresh slots are pushed once), without a 23 M-entry heap whose sift-downs miss the cache.
 	struct WorkList {
 		std::map<float, std::vector<int>> later;	// areas below the loaded bucket
